@@ -1,0 +1,150 @@
+/* cmax_b200.h - C ABI of the B200-native contrast-maximisation (CMax) loss path.
+ *
+ * Drop-in boundary for tub-rip/MotionPriorCMax's loss plugin (upstream file:line cited per
+ * entry point).  Plain pointers and sizes only: no torch types, no C++ in the signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; all tensors are dense,
+ *     row-major, float32 unless stated; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises, nothing allocates: scratch comes from the caller's
+ *     `workspace` (size from cmax_workspace_bytes, 256-byte aligned base);
+ *   - return value: CMAX_OK (0) or a negative CMAX_ERR_* code; never throws;
+ *   - coordinates are (y, x); events are rows of 6 floats (y, x, t, p, bin, valid) with the
+ *     positives first when polarity-aware (upstream src/loader/dsec/loader.py:156-161,360-415).
+ */
+#ifndef CMAX_B200_H_
+#define CMAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMAX_ABI_VERSION 1
+
+enum {
+    CMAX_OK = 0,
+    CMAX_ERR_BAD_CONFIG = -1,   /* a CmaxConfig field is out of range / forbidden combination */
+    CMAX_ERR_BAD_SHAPE = -2,    /* B, M, n, num_pos_events inconsistent                          */
+    CMAX_ERR_WORKSPACE = -3,    /* workspace NULL, misaligned or smaller than required           */
+    CMAX_ERR_CUDA = -4,         /* a CUDA launch failed (cudaGetLastError is left set)           */
+    CMAX_ERR_UNSUPPORTED = -5   /* valid but not implemented size (e.g. num_knn too large)       */
+};
+
+/* norms / schemes */
+enum { CMAX_NORM_L1 = 0, CMAX_NORM_L2 = 1 };
+enum { CMAX_INTERP_MEAN = 0, CMAX_INTERP_IWD = 1 };
+enum { CMAX_SMOOTH_ON_FLOW_TO_TREF = 0, CMAX_SMOOTH_ON_FLOW_TO_NEXT = 1 };
+enum { CMAX_BASIS_POLYNOMIAL = 0, CMAX_BASIS_DCT = 1, CMAX_BASIS_BEZIER = 2 };
+
+/* Mirrors the keyword arguments of upstream FocusLoss.__init__ (src/losses/focus.py:28-51). */
+typedef struct CmaxConfig {
+    int32_t height, width;            /* image_shape                                        */
+    int32_t num_tref;                 /* R >= 1                                             */
+    int32_t num_bins;                 /* nb >= 1                                            */
+    int32_t num_knn;                  /* K >= 1, K <= n                                     */
+    int32_t lut_superpixel_size;      /* s >= 1                                             */
+    int32_t focus_loss_norm;          /* CMAX_NORM_L1 | CMAX_NORM_L2                        */
+    int32_t dist_norm;                /* CMAX_NORM_L1 | CMAX_NORM_L2                        */
+    int32_t scale_iwe_by_dt;          /* bool; requires num_tref == 1 (focus.py:49)         */
+    int32_t mask_image_border;        /* bool                                               */
+    int32_t polarity_aware_batching;  /* bool; requires num_tref == 1 (focus.py:50)         */
+    int32_t interpolation_scheme;     /* CMAX_INTERP_MEAN | CMAX_INTERP_IWD                 */
+    int32_t smooth_type;              /* on_flow_to_next requires num_tref == 1 (focus.py:51) */
+    float smooth_weight;
+    int32_t deterministic;            /* 1: IWE and LUT-gradient accumulate in int64 fixed point
+                                         (run-to-run bit-identical); 0: float32 atomics          */
+    int32_t reserved[3];
+} CmaxConfig;
+
+int cmax_abi_version(void);
+const char *cmax_error_string(int code);
+
+/* Scratch bytes cmax_forward / cmax_backward need for a batch of B windows of M event rows and
+ * n trajectories.  Returns 0 on an invalid configuration.  The same workspace must be handed,
+ * untouched, from cmax_forward to the matching cmax_backward (it carries the saved context). */
+size_t cmax_workspace_bytes(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n);
+
+/* Forward of upstream FocusLoss.calc (src/losses/focus.py:66-113): interpolate_flow (:115-180),
+ * warp_events (:182-195), make_iwes (:197-230) -> create_iwe (src/utils/event_image_converter.py
+ * :45-74,333-391 + gaussian blur :170-175), calculate_focus_loss (src/utils/loss.py:4-27) and
+ * calculate_smooth_loss (focus.py:232-246, loss.py:29-56).
+ *
+ *   trajectories [B, R + nb, n, 2]   times [R + nb]   events [B, M, 6]
+ *   num_pos_events: split index of the polarity-aware layout (ignored otherwise; must be
+ *                   0..M when polarity_aware_batching)
+ *   iwes_out   [B * R, P, H, W]  blurred IWEs, P = 2 if polarity aware else 1
+ *   losses_out [3] = {loss, focus_loss, smoothness_loss}
+ *   flow_lut_out (optional, may be NULL) [B, nb, H/s, W/s, R, 2]
+ */
+int cmax_forward(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                 const float *events, int64_t B, int64_t M, int64_t n, int64_t num_pos_events,
+                 float *iwes_out, float *losses_out, float *flow_lut_out,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of the same call: d loss / d trajectories, scaled by *grad_loss (device scalar).
+ *   dtraj_out [B, R + nb, n, 2] is fully overwritten.
+ * Inputs must be the ones given to the cmax_forward that filled `workspace`. */
+int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                  const float *events, int64_t B, int64_t M, int64_t n, int64_t num_pos_events,
+                  const float *grad_loss, float *dtraj_out,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* Stand-alone imager, upstream EventImageConverter.create_iwe(events, method='bilinear_vote',
+ * sigma, weight) (src/utils/event_image_converter.py:45-74,134-176,333-391).
+ *   events [nb, M, row_stride] (first two columns y, x; row_stride >= 2 floats)
+ *   weight NULL (-> 1.0) or [nb, M];  sigma 0 (no blur) or > 0 (3x3 gaussian, reflect pad)
+ *   out [nb, H, W];  scratch: NULL when sigma == 0, else nb*H*W floats.
+ *   deterministic: accumulate in int64 fixed point (scratch_i64 [nb*H*W] required). */
+int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_t M,
+                    int64_t row_stride, int32_t H, int32_t W, float sigma, float *out,
+                    float *scratch, int64_t *scratch_i64, int32_t deterministic, void *stream);
+
+/* Event-count image, upstream count_event_tensor (event_image_converter.py:226-272): four unit
+ * votes per event at the bilinear corners, exact integers.  out [nb, H, W] int64. */
+int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride,
+                     int32_t H, int32_t W, int64_t *out, void *stream);
+
+/* Test / inspection entry: the K nearest trajectories of every LUT cell exactly as cmax_forward
+ * selects them (focus.py:128-137), ascending distance, lowest index first on ties.
+ *   points [S, n, 2] (S independent slabs = B * nb);  ind_out [S, q, K] int32;
+ *   dist_out (optional) [S, q, K].  workspace: cmax_knn_workspace_bytes. */
+size_t cmax_knn_workspace_bytes(int32_t H, int32_t W, int32_t s, int64_t S, int64_t n, int32_t K);
+int cmax_knn_indices(const float *points, int64_t S, int64_t n, int32_t H, int32_t W, int32_t s,
+                     int32_t K, int32_t dist_norm, int32_t *ind_out, float *dist_out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused front end, upstream TrajectoryNet.calculate_trajectories_at_t
+ * (src/modules/trajectory_net.py:101-119) = coeffs_grid_to_list (src/utils/trajectories.py:15-52)
+ * + compute_basis (src/utils/basis.py:4-46), and the Bezier basis of
+ * src/models/raft_spline/curves/bezier.py:68-113.
+ *   coeff_grid [B, S, 2K, H, W]; channel c < K -> first axis, c >= K -> second axis; axis order
+ *   (y, x) unless xy_order != 0 (RAFT-spline stores x first);  basis_table host-independent:
+ *   phi [n_t, K] DEVICE table of (phi_k(t) - phi_k(anchor)) built by the caller;
+ *   trajectories_out [B, n_t, n, 2] with n = ceil((H - p/2)/p) * ceil((W - p/2)/p) tile centres. */
+int cmax_trajectories_forward(const float *coeff_grid, const float *phi, int64_t B, int64_t S,
+                              int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
+                              int32_t xy_order, int32_t add_offsets, float *trajectories_out,
+                              void *stream);
+/* Adjoint: d coeff_grid [B, S, 2K, H, W] (dense, zero away from the tile centres). */
+int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, int64_t S,
+                               int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
+                               int32_t xy_order, float *dcoeff_grid_out, void *stream);
+
+/* Micro-benchmark used by bench.py to measure the atomic side of the roofline on the box:
+ * n_ops float32 `red.global.add` to pseudo-random addresses inside `region_floats` floats.
+ * mode 0: global red.f32, 1: shared-memory atomics + flush, 2: global red on int64. */
+int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, int32_t mode,
+                           void *stream);
+
+/* Reads the status words the kernels keep in the workspace (host call, synchronises `stream`):
+ * out[0] = events skipped because their LUT cell index was out of range, out[1..3] reserved. */
+int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMAX_B200_H_ */

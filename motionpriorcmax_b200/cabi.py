@@ -1,0 +1,127 @@
+"""ctypes binding of the C-ABI library (include/cmax_b200.h).
+
+The product path has no CPU fallback: if ``libcmax_b200.so`` is missing or a call returns an
+error code, a ``RuntimeError`` is raised.  PyTorch only supplies device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_lib", "libcmax_b200.so")
+
+NORM = {"l1": 0, "l2": 1}
+INTERP = {"mean": 0, "iwd": 1}
+SMOOTH = {"on_flow_to_tref": 0, "on_flow_to_next": 1}
+
+EXPORTS = (
+    "cmax_abi_version", "cmax_error_string", "cmax_workspace_bytes", "cmax_forward",
+    "cmax_backward", "cmax_create_iwe", "cmax_count_image", "cmax_knn_workspace_bytes",
+    "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
+    "cmax_atomic_microbench", "cmax_read_status",
+)
+
+
+class CmaxConfig(Structure):
+    _fields_ = [
+        ("height", c_int32), ("width", c_int32), ("num_tref", c_int32), ("num_bins", c_int32),
+        ("num_knn", c_int32), ("lut_superpixel_size", c_int32), ("focus_loss_norm", c_int32),
+        ("dist_norm", c_int32), ("scale_iwe_by_dt", c_int32), ("mask_image_border", c_int32),
+        ("polarity_aware_batching", c_int32), ("interpolation_scheme", c_int32),
+        ("smooth_type", c_int32), ("smooth_weight", c_float), ("deterministic", c_int32),
+        ("reserved", c_int32 * 3),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m motionpriorcmax_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the CMax loss path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    P = c_void_p
+    lib.cmax_abi_version.restype = c_int32
+    lib.cmax_error_string.restype = c_char_p
+    lib.cmax_error_string.argtypes = [c_int32]
+    lib.cmax_workspace_bytes.restype = c_size_t
+    lib.cmax_workspace_bytes.argtypes = [POINTER(CmaxConfig), c_int64, c_int64, c_int64]
+    lib.cmax_forward.restype = c_int32
+    lib.cmax_forward.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, c_int64, c_int64,
+                                 P, P, P, P, c_size_t, P]
+    lib.cmax_backward.restype = c_int32
+    lib.cmax_backward.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, c_int64, c_int64,
+                                  P, P, P, c_size_t, P]
+    lib.cmax_create_iwe.restype = c_int32
+    lib.cmax_create_iwe.argtypes = [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_float, P,
+                                    P, P, c_int32, P]
+    lib.cmax_count_image.restype = c_int32
+    lib.cmax_count_image.argtypes = [P, c_int64, c_int64, c_int64, c_int32, c_int32, P, P]
+    lib.cmax_knn_workspace_bytes.restype = c_size_t
+    lib.cmax_knn_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int64, c_int64, c_int32]
+    lib.cmax_knn_indices.restype = c_int32
+    lib.cmax_knn_indices.argtypes = [P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, P, P, P, c_size_t, P]
+    lib.cmax_trajectories_forward.restype = c_int32
+    lib.cmax_trajectories_forward.argtypes = [P, P, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                              c_int32, c_int32, c_int32, c_int32, P, P]
+    lib.cmax_trajectories_backward.restype = c_int32
+    lib.cmax_trajectories_backward.argtypes = [P, P, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                               c_int32, c_int32, c_int32, P, P]
+    lib.cmax_atomic_microbench.restype = c_int32
+    lib.cmax_atomic_microbench.argtypes = [P, c_int64, c_int64, c_int32, P]
+    lib.cmax_read_status.restype = c_int32
+    lib.cmax_read_status.argtypes = [P, POINTER(c_int64 * 4), P]
+    if lib.cmax_abi_version() != 1:
+        raise RuntimeError("libcmax_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cmax_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_superpixel_size,
+                focus_loss_norm, dist_norm, scale_iwe_by_dt, mask_image_border,
+                polarity_aware_batching, interpolation_scheme, smooth_type,
+                deterministic=False) -> CmaxConfig:
+    for name, table, val in (("focus_loss_norm", NORM, focus_loss_norm),
+                             ("dist_norm", NORM, dist_norm),
+                             ("interpolation_scheme", INTERP, interpolation_scheme),
+                             ("smooth_type", SMOOTH, smooth_type)):
+        if val not in table:
+            raise ValueError(f"{name}={val!r} not in {sorted(table)}")
+    c = CmaxConfig()
+    c.height, c.width = int(image_shape[0]), int(image_shape[1])
+    c.num_tref, c.num_bins, c.num_knn = int(num_tref), int(num_bins), int(num_knn)
+    c.lut_superpixel_size = int(lut_superpixel_size)
+    c.focus_loss_norm, c.dist_norm = NORM[focus_loss_norm], NORM[dist_norm]
+    c.scale_iwe_by_dt = int(bool(scale_iwe_by_dt))
+    c.mask_image_border = int(bool(mask_image_border))
+    c.polarity_aware_batching = int(bool(polarity_aware_batching))
+    c.interpolation_scheme = INTERP[interpolation_scheme]
+    c.smooth_type = SMOOTH[smooth_type]
+    c.smooth_weight = float(smooth_weight)
+    c.deterministic = int(bool(deterministic))
+    return c
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a torch tensor (or NULL)."""
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr(device) -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,483 @@
+// api.cu - the extern "C" boundary declared in include/cmax_b200.h, geometry / workspace
+// layout, the fused coeff_grid -> trajectories front end and the atomic micro-benchmark.
+#include <string.h>
+
+#include "cmax_common.cuh"
+
+namespace cmax {
+
+int launch_splat(int mode, const float *events, const float *weight, int64_t nb, int64_t M,
+                 int64_t stride, int H, int W, float *out, long long *out_i64, cudaStream_t st);
+int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStream_t st);
+int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
+                cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g)
+{
+    g->H = H;
+    g->W = W;
+    g->s = s;
+    g->K = K;
+    g->n = n;
+    g->Hq = (H + s - 1) / s;                    // len(arange(0, H, s)), focus.py:118-124
+    g->Wq = (W + s - 1) / s;
+    g->q = g->Hq * g->Wq;
+    g->off = (float)s / 2.0f - 0.5f;
+    // cell edge: the smallest multiple of s with at most kMaxCells cells and, for sparse point
+    // sets, roughly one point per cell or more
+    int m = 1;
+    while (true) {
+        int cs = s * m;
+        int64_t nc = (int64_t)((H + cs - 1) / cs) * ((W + cs - 1) / cs);
+        double per_cell = (double)n / (double)nc;
+        if (nc <= kMaxCells && (per_cell >= 0.75 || nc <= 64)) break;
+        ++m;
+    }
+    g->cs = (float)(s * m);
+    g->inv_cs = 1.0f / g->cs;
+    g->Hc = (H + s * m - 1) / (s * m);
+    g->Wc = (W + s * m - 1) / (s * m);
+    g->NC = g->Hc * g->Wc;
+    // initial window: radius that holds K points at the mean density
+    double dens = (double)n / ((double)H * W);
+    double rk = sqrt((double)K / (3.14159265358979 * (dens > 0 ? dens : 1e-9)));
+    int r0 = (int)ceil((rk - 0.5 * g->cs) / g->cs);
+    g->r0 = r0 < 0 ? 0 : (r0 > 8 ? 8 : r0);
+}
+
+int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos, Geom *g)
+{
+    if (!c) return CMAX_ERR_BAD_CONFIG;
+    if (c->height < 3 || c->width < 3 || c->num_tref < 1 || c->num_bins < 1 || c->num_knn < 1 ||
+        c->lut_superpixel_size < 1)
+        return CMAX_ERR_BAD_CONFIG;
+    if ((unsigned)c->focus_loss_norm > 1u || (unsigned)c->dist_norm > 1u ||
+        (unsigned)c->interpolation_scheme > 1u || (unsigned)c->smooth_type > 1u)
+        return CMAX_ERR_BAD_CONFIG;
+    // focus.py:49-51
+    if (c->num_tref != 1 && (c->scale_iwe_by_dt || c->polarity_aware_batching ||
+                             c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT))
+        return CMAX_ERR_BAD_CONFIG;
+    if (B < 1 || M < 0 || n < 1) return CMAX_ERR_BAD_SHAPE;
+    if (c->num_knn > n) return CMAX_ERR_BAD_SHAPE;
+    if (c->polarity_aware_batching && (npos < 0 || npos > M)) return CMAX_ERR_BAD_SHAPE;
+    if (c->num_knn > kMaxKnn || c->num_tref > kMaxTref) return CMAX_ERR_UNSUPPORTED;
+    if (B > 65535 || n > (int64_t)INT32_MAX / 2 || B * c->num_bins > (int64_t)INT32_MAX)
+        return CMAX_ERR_UNSUPPORTED;
+    memset(g, 0, sizeof(*g));
+    knn_geom(c->height, c->width, c->lut_superpixel_size, n, c->num_knn, g);
+    g->R = c->num_tref;
+    g->nb = c->num_bins;
+    g->P = c->polarity_aware_batching ? 2 : 1;
+    g->l1dist = c->dist_norm == CMAX_NORM_L1;
+    g->l2focus = c->focus_loss_norm == CMAX_NORM_L2;
+    g->scale_dt = c->scale_iwe_by_dt != 0;
+    g->mask_border = c->mask_image_border != 0;
+    g->pab = c->polarity_aware_batching != 0;
+    g->iwd = c->interpolation_scheme == CMAX_INTERP_IWD && c->num_knn > 1;    // focus.py:145-163
+    g->smooth_next = c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT;
+    g->det = c->deterministic != 0;
+    g->smooth_w = c->smooth_weight;
+    g->B = B;
+    g->M = M;
+    g->S = B * c->num_bins;
+    g->npos = npos;
+    return CMAX_OK;
+}
+
+Layout make_layout(const Geom &g)
+{
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    const int64_t planes = g.B * g.R * g.P;
+    const int64_t npix = planes * (int64_t)g.H * g.W;
+    const int64_t nlut = g.S * g.q * g.R * 2;
+    const int64_t nf2n = g.smooth_next ? g.B * (g.nb - 1) * g.q * 2 : 0;
+    L.n_img_blocks = (int)(planes * ((g.H + kImgTile - 1) / kImgTile) * ((g.W + kImgTile - 1) / kImgTile));
+    const int64_t sm_imgs = g.smooth_next ? g.B * (g.nb - 1) : g.S * g.R;
+    L.n_sm_blocks = (int)(sm_imgs * ((g.Wq + 31) / 32) * ((g.Hq + 7) / 8));
+    L.header = take(1024);
+    L.focus_partials = take(sizeof(double) * L.n_img_blocks);
+    L.smooth_partials = take(sizeof(double) * (L.n_sm_blocks > 0 ? L.n_sm_blocks : 1));
+    L.cell_start = take(sizeof(int) * g.S * (g.NC + 1));
+    L.sorted = take(sizeof(float4) * g.S * g.n);
+    L.tau = take(sizeof(float) * g.S * g.q);
+    L.jcut = take(sizeof(int) * g.S * g.q);
+    L.wsum = take(g.iwd ? sizeof(float) * g.S * g.q : 16);
+    L.tau_max = take(sizeof(unsigned) * g.S);
+    L.lut = take(sizeof(float) * nlut);
+    L.f2n = take(sizeof(float) * (nf2n > 0 ? nf2n : 4));
+    L.raw = take(sizeof(float) * npix);
+    L.raw_i64 = take(g.det ? sizeof(long long) * npix : 16);
+    L.dimg = take(sizeof(float) * npix);
+    L.dlut = take(sizeof(float) * nlut);
+    L.dlut_i64 = take(g.det ? sizeof(long long) * nlut : 16);
+    L.df2n = take(sizeof(float) * (nf2n > 0 ? nf2n : 4));
+    L.total = off;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// front end: coeff_grid -> trajectories (trajectory_net.py:101-119) and its adjoint
+// ---------------------------------------------------------------------------------------------
+// one thread per (b, tile j): K coefficients per axis in registers, basis table phi[n_t, K]
+// (already phi(t) - phi(anchor)) broadcast from shared memory.
+constexpr int kMaxBasis = 16;
+
+__global__ void __launch_bounds__(128)
+traj_forward_kernel(const float *__restrict__ cg, const float *__restrict__ phi, int64_t S, int K,
+                    int H, int W, int patch, int ny, int nx, int n_t, int xy, int add_off,
+                    float *__restrict__ out)
+{
+    extern __shared__ float s_phi[];
+    for (int i = threadIdx.x; i < n_t * K; i += blockDim.x) s_phi[i] = phi[i];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t n = (int64_t)ny * nx;
+    if (j >= n) return;
+    const int ty = (int)(j / nx), tx = (int)(j - (int64_t)ty * nx);
+    const int py = patch / 2 + ty * patch, px = patch / 2 + tx * patch;     // trajectories.py:8-13
+    float cy[kMaxBasis], cx[kMaxBasis];
+    const int64_t HW = (int64_t)H * W;
+#pragma unroll
+    for (int k = 0; k < kMaxBasis; ++k) {
+        if (k < K) {
+            float a0 = 0.0f, a1 = 0.0f;
+            for (int64_t sc = 0; sc < S; ++sc) {                        // sum over scales (basis.py:46)
+                const float *base = cg + ((b * S + sc) * 2 * K) * HW + (int64_t)py * W + px;
+                a0 += __ldg(base + (int64_t)k * HW);
+                a1 += __ldg(base + (int64_t)(K + k) * HW);
+            }
+            cy[k] = xy ? a1 : a0;
+            cx[k] = xy ? a0 : a1;
+        }
+    }
+    float2 *o = reinterpret_cast<float2 *>(out) + b * (int64_t)n_t * n + j;
+    for (int t = 0; t < n_t; ++t) {
+        float y = 0.0f, x = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxBasis; ++k)
+            if (k < K) {
+                y += s_phi[t * K + k] * cy[k];
+                x += s_phi[t * K + k] * cx[k];
+            }
+        if (add_off) { y += (float)py; x += (float)px; }
+        o[(int64_t)t * n] = make_float2(y, x);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+traj_backward_kernel(const float *__restrict__ dtraj, const float *__restrict__ phi, int64_t S,
+                     int K, int H, int W, int patch, int ny, int nx, int n_t, int xy,
+                     float *__restrict__ dcg)
+{
+    extern __shared__ float s_phi[];
+    for (int i = threadIdx.x; i < n_t * K; i += blockDim.x) s_phi[i] = phi[i];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t n = (int64_t)ny * nx;
+    if (j >= n) return;
+    const int ty = (int)(j / nx), tx = (int)(j - (int64_t)ty * nx);
+    const int py = patch / 2 + ty * patch, px = patch / 2 + tx * patch;
+    float gy[kMaxBasis], gx[kMaxBasis];
+#pragma unroll
+    for (int k = 0; k < kMaxBasis; ++k) gy[k] = gx[k] = 0.0f;
+    const float2 *d = reinterpret_cast<const float2 *>(dtraj) + b * (int64_t)n_t * n + j;
+    for (int t = 0; t < n_t; ++t) {
+        const float2 v = __ldg(d + (int64_t)t * n);
+#pragma unroll
+        for (int k = 0; k < kMaxBasis; ++k)
+            if (k < K) {
+                gy[k] += s_phi[t * K + k] * v.x;
+                gx[k] += s_phi[t * K + k] * v.y;
+            }
+    }
+    const int64_t HW = (int64_t)H * W;
+#pragma unroll
+    for (int k = 0; k < kMaxBasis; ++k) {
+        if (k < K) {
+            for (int64_t sc = 0; sc < S; ++sc) {
+                float *base = dcg + ((b * S + sc) * 2 * K) * HW + (int64_t)py * W + px;
+                base[(int64_t)k * HW] = xy ? gx[k] : gy[k];
+                base[(int64_t)(K + k) * HW] = xy ? gy[k] : gx[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// atomic micro-benchmark
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+atomic_bench_kernel(float *region, unsigned region_floats, int64_t n_ops)
+{
+    __shared__ float s_tile[MODE == 1 ? 12288 : 1];
+    if (MODE == 1) {
+        for (int i = threadIdx.x; i < 12288; i += blockDim.x) s_tile[i] = 0.0f;
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n_ops; i += stride) {
+        unsigned h = hash32((unsigned)i * 2654435761u + 12345u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // mimic a bilinear vote: (p, p+1, p+W, p+W+1) with W = 640
+            unsigned a = (h % (region_floats - 642u)) + (k & 1) + (k >> 1) * 640u;
+            if (MODE == 0) atomicAdd(region + a, 1.0f);
+            if (MODE == 1) atomicAdd(&s_tile[a % 12288u], 1.0f);
+            if (MODE == 2)
+                atomicAdd(reinterpret_cast<unsigned long long *>(region) + (a >> 1), 1ull);
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 12288; i += blockDim.x)
+            if (s_tile[i] != 0.0f) atomicAdd(region + (i % region_floats), s_tile[i]);
+    }
+}
+
+}  // namespace cmax
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+using namespace cmax;
+
+extern "C" {
+
+int cmax_abi_version(void) { return CMAX_ABI_VERSION; }
+
+const char *cmax_error_string(int code)
+{
+    switch (code) {
+    case CMAX_OK: return "ok";
+    case CMAX_ERR_BAD_CONFIG: return "invalid CmaxConfig (range, or a combination upstream focus.py:49-51 forbids)";
+    case CMAX_ERR_BAD_SHAPE: return "inconsistent B / M / n / num_pos_events / num_knn";
+    case CMAX_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+    case CMAX_ERR_CUDA: return "CUDA launch failure";
+    case CMAX_ERR_UNSUPPORTED: return "size not supported by this build (num_knn <= 192, num_tref <= 16, B <= 65535)";
+    default: return "unknown error";
+    }
+}
+
+size_t cmax_workspace_bytes(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n)
+{
+    Geom g;
+    if (make_geom(cfg, B, M, n, 0, &g) != CMAX_OK) return 0;
+    return make_layout(g).total;
+}
+
+int cmax_forward(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                 const float *events, int64_t B, int64_t M, int64_t n, int64_t num_pos_events,
+                 float *iwes_out, float *losses_out, float *flow_lut_out, void *workspace,
+                 size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!trajectories || !times || (!events && M > 0) || !iwes_out || !losses_out)
+        return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(ws + L.header, 0, 1024, st);
+    if ((rc = launch_lut_forward(g, L, trajectories, ws, flow_lut_out, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_event_forward(g, L, events, times, ws, st))) return rc;
+    if ((rc = launch_image_forward(g, L, ws, iwes_out, st))) return rc;
+    if ((rc = launch_smooth_forward(g, L, ws, st))) return rc;
+    return launch_finalize_losses(g, L, ws, losses_out, st);
+}
+
+int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                  const float *events, int64_t B, int64_t M, int64_t n, int64_t num_pos_events,
+                  const float *grad_loss, float *dtraj_out, void *workspace,
+                  size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!trajectories || !times || (!events && M > 0) || !grad_loss || !dtraj_out)
+        return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_image_backward(g, L, ws, st))) return rc;
+    if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
+    if ((rc = launch_event_backward(g, L, events, times, grad_loss, ws, st))) return rc;
+    return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
+}
+
+int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_t M,
+                    int64_t row_stride, int32_t H, int32_t W, float sigma, float *out,
+                    float *scratch, int64_t *scratch_i64, int32_t deterministic, void *stream)
+{
+    if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
+        return CMAX_ERR_BAD_SHAPE;
+    if (sigma > 0.0f && (!scratch || H < 2 || W < 2)) return CMAX_ERR_WORKSPACE;
+    if (deterministic && !scratch_i64) return CMAX_ERR_WORKSPACE;
+    if (nb > 65535) return CMAX_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t count = nb * (int64_t)H * W;
+    if (count == 0) return CMAX_OK;
+    float *raw = sigma > 0.0f ? scratch : out;
+    int rc;
+    if (deterministic) {
+        cudaMemsetAsync(scratch_i64, 0, sizeof(long long) * count, st);
+        if ((rc = launch_splat(1, events, weight, nb, M, row_stride, H, W, nullptr,
+                               reinterpret_cast<long long *>(scratch_i64), st))) return rc;
+        if ((rc = launch_fix_to_float(reinterpret_cast<long long *>(scratch_i64), raw, count, st))) return rc;
+    } else {
+        cudaMemsetAsync(raw, 0, sizeof(float) * count, st);
+        if ((rc = launch_splat(0, events, weight, nb, M, row_stride, H, W, raw, nullptr, st))) return rc;
+    }
+    if (sigma > 0.0f) return launch_blur(raw, out, nb, H, W, sigma, st);
+    return check_launch();
+}
+
+int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride, int32_t H,
+                     int32_t W, int64_t *out, void *stream)
+{
+    if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
+        return CMAX_ERR_BAD_SHAPE;
+    if (nb > 65535) return CMAX_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(out, 0, sizeof(long long) * nb * (int64_t)H * W, st);
+    return launch_splat(2, events, nullptr, nb, M, row_stride, H, W, nullptr,
+                        reinterpret_cast<long long *>(out), st);
+}
+
+static int knn_only_geom(int32_t H, int32_t W, int32_t s, int64_t S, int64_t n, int32_t K, Geom *g)
+{
+    if (H < 1 || W < 1 || s < 1 || S < 1 || n < 1 || K < 1 || K > n) return CMAX_ERR_BAD_SHAPE;
+    if (K > kMaxKnn || S > 65535) return CMAX_ERR_UNSUPPORTED;
+    memset(g, 0, sizeof(*g));
+    knn_geom(H, W, s, n, K, g);
+    g->R = 0;
+    g->nb = (int)S;
+    g->B = 1;
+    g->S = S;
+    g->P = 1;
+    return CMAX_OK;
+}
+
+size_t cmax_knn_workspace_bytes(int32_t H, int32_t W, int32_t s, int64_t S, int64_t n, int32_t K)
+{
+    Geom g;
+    if (knn_only_geom(H, W, s, S, n, K, &g) != CMAX_OK) return 0;
+    return align_up(sizeof(int) * S * (g.NC + 1)) + align_up(sizeof(float4) * S * n);
+}
+
+int cmax_knn_indices(const float *points, int64_t S, int64_t n, int32_t H, int32_t W, int32_t s,
+                     int32_t K, int32_t dist_norm, int32_t *ind_out, float *dist_out,
+                     void *workspace, size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = knn_only_geom(H, W, s, S, n, K, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!points || !ind_out) return CMAX_ERR_BAD_SHAPE;
+    g.l1dist = dist_norm == CMAX_NORM_L1;
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    L.cell_start = 0;
+    L.sorted = align_up(sizeof(int) * S * (g.NC + 1));
+    if (!workspace || ((uintptr_t)workspace & 255u) ||
+        workspace_bytes < L.sorted + align_up(sizeof(float4) * S * n))
+        return CMAX_ERR_WORKSPACE;
+    return launch_lut_forward(g, L, points, static_cast<char *>(workspace), nullptr, ind_out,
+                              dist_out, static_cast<cudaStream_t>(stream));
+}
+
+static int traj_check(int64_t B, int64_t S, int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t)
+{
+    if (B < 1 || S < 1 || K < 1 || H < 1 || W < 1 || patch < 1 || n_t < 1) return CMAX_ERR_BAD_SHAPE;
+    if (patch / 2 >= H || patch / 2 >= W) return CMAX_ERR_BAD_SHAPE;
+    if (K > kMaxBasis || B > 65535 || (size_t)n_t * K * 4 > 48 * 1024) return CMAX_ERR_UNSUPPORTED;
+    return CMAX_OK;
+}
+
+int cmax_trajectories_forward(const float *coeff_grid, const float *phi, int64_t B, int64_t S,
+                              int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
+                              int32_t xy_order, int32_t add_offsets, float *trajectories_out,
+                              void *stream)
+{
+    int rc = traj_check(B, S, K, H, W, patch, n_t);
+    if (rc) return rc;
+    if (!coeff_grid || !phi || !trajectories_out) return CMAX_ERR_BAD_SHAPE;
+    const int o = patch / 2;
+    const int ny = (H - o + patch - 1) / patch, nx = (W - o + patch - 1) / patch;
+    dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
+    traj_forward_kernel<<<grid, 128, sizeof(float) * n_t * K, static_cast<cudaStream_t>(stream)>>>(
+        coeff_grid, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, add_offsets, trajectories_out);
+    return check_launch();
+}
+
+int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, int64_t S,
+                               int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
+                               int32_t xy_order, float *dcoeff_grid_out, void *stream)
+{
+    int rc = traj_check(B, S, K, H, W, patch, n_t);
+    if (rc) return rc;
+    if (!dtraj || !phi || !dcoeff_grid_out) return CMAX_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int o = patch / 2;
+    const int ny = (H - o + patch - 1) / patch, nx = (W - o + patch - 1) / patch;
+    cudaMemsetAsync(dcoeff_grid_out, 0, sizeof(float) * B * S * 2 * K * (int64_t)H * W, st);
+    dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
+    traj_backward_kernel<<<grid, 128, sizeof(float) * n_t * K, st>>>(
+        dtraj, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, dcoeff_grid_out);
+    return check_launch();
+}
+
+int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, int32_t mode,
+                           void *stream)
+{
+    if (!region || region_floats < 1024 || region_floats > 0x7fffffff || n_ops < 0)
+        return CMAX_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = 148 * 8;
+    if (mode == 0)
+        atomic_bench_kernel<0><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
+    else if (mode == 1)
+        atomic_bench_kernel<1><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
+    else if (mode == 2)
+        atomic_bench_kernel<2><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
+    else
+        return CMAX_ERR_BAD_CONFIG;
+    return check_launch();
+}
+
+int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream)
+{
+    if (!workspace || !out_host) return CMAX_ERR_WORKSPACE;
+    long long tmp[4];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(tmp, workspace, sizeof(tmp), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return CMAX_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return CMAX_ERR_CUDA;
+    for (int i = 0; i < 4; ++i) out_host[i] = tmp[i];
+    return CMAX_OK;
+}
+
+}  // extern "C"

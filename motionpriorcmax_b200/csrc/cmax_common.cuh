@@ -1,0 +1,182 @@
+// cmax_common.cuh - shared declarations of the B200 (sm_100a) CMax loss kernels.
+//
+// Data layout in HBM (all float32 unless noted, row-major):
+//   trajectories [B, R+nb, n, 2]      (y, x) absolute pixel positions, caller owned
+//   events       [B, M, 6]            (y, x, t, p, bin, valid), caller owned
+//   workspace    one caller-owned slab carved by `Layout` below: LUT, per-cell KNN
+//                thresholds, raw IWE, dL/dIWE, dLUT ...
+// "slab" = one (sample, time-bin) pair: S = B * nb independent KNN problems.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/cmax_b200.h"
+
+namespace cmax {
+
+constexpr int kMaxCells = 24576;      // cell-list cells per slab (smem counters, 96 KB)
+constexpr int kMaxTref = 16;          // reference times handled by the gather kernels
+constexpr int kKnnBlock = 128;        // threads per KNN CTA (one LUT query per thread)
+constexpr int kKnnTileW = 16;         // KNN CTA = 16 x 8 queries
+constexpr int kKnnTileH = 8;
+constexpr int kMaxKnn = 192;          // heap lives in shared memory: 8 B * K * 128 threads
+constexpr int kImgTile = 32;          // image-stage CTA tile (32 x 32 pixels, 256 threads)
+constexpr double kFixScale = 4294967296.0;   // 2^32: int64 fixed-point scale (deterministic mode)
+constexpr float kVoteEps = 1e-6f;     // event_image_converter.py:357
+constexpr float kIwdEps = 1e-9f;      // focus.py:7
+constexpr float kCharbEps2 = 1e-6f;   // (1e-3)^2, loss.py:46,55
+
+struct Geom {                 // derived sizes, passed by value to kernels
+    int H, W, R, nb, K, s, P;
+    int Hq, Wq, q;            // LUT lattice
+    float off;                // s/2 - 0.5 (focus.py:117)
+    int Hc, Wc, NC;           // cell list
+    float cs, inv_cs;         // cell edge (multiple of s)
+    int r0;                   // initial search radius in cells
+    int l1dist, l2focus, scale_dt, mask_border, pab, iwd, smooth_next, det;
+    float smooth_w;
+    int64_t B, M, n, S;       // S = B * nb
+    int64_t npos;
+};
+
+struct Header {               // first 1 KiB of the workspace
+    long long status[4];      // [0] events skipped: LUT cell out of range
+    double focus_sum;         // sum of |dx|+|dy| (or squares) over all IWE pixels
+    double smooth_sum;        // sum of charbonnier terms (x and y)
+    float val;                // focus_sum / N
+    float focus, smooth, loss;
+    int n_focus_partials, n_smooth_partials;
+};
+
+struct Layout {
+    size_t header, focus_partials, smooth_partials, cell_start, sorted, tau, jcut, wsum, tau_max,
+        lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
+    int n_img_blocks, n_sm_blocks;
+};
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int make_geom(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, int64_t npos, Geom *g);
+void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g);
+Layout make_layout(const Geom &g);
+
+// ---- launchers (each returns cudaGetLastError() != cudaSuccess ? CMAX_ERR_CUDA : CMAX_OK) ----
+int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,
+                       float *flow_lut_out, int32_t *ind_out, float *dist_out, cudaStream_t st);
+int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
+                        float *dtraj, cudaStream_t st);
+int launch_event_forward(const Geom &g, const Layout &L, const float *events, const float *times,
+                         char *ws, cudaStream_t st);
+int launch_event_backward(const Geom &g, const Layout &L, const float *events, const float *times,
+                          const float *grad_loss, char *ws, cudaStream_t st);
+int launch_image_forward(const Geom &g, const Layout &L, char *ws, float *iwes_out, cudaStream_t st);
+int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
+int launch_smooth_forward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
+int launch_smooth_backward(const Geom &g, const Layout &L, const float *grad_loss, char *ws,
+                           cudaStream_t st);
+int launch_finalize_losses(const Geom &g, const Layout &L, char *ws, float *losses_out,
+                           cudaStream_t st);
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? CMAX_OK : CMAX_ERR_CUDA; }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+// Streaming 8-byte load that does not allocate in L1 (the event stream is read exactly once;
+// L1 is kept for the LUT slab and the dL/dIWE gathers).
+__device__ __forceinline__ float2 ld_stream_f2(const float *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];"
+                 : "=f"(r.x), "=f"(r.y)
+                 : "l"(p));
+    return r;
+}
+
+// Python-style float floor division, the arithmetic of torch's `//` on float tensors
+// (c10 div_floor_floating) used by focus.py:186-187.
+__device__ __forceinline__ float floordiv_f32(float a, float b)
+{
+    float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div = __fsub_rn(div, 1.0f);
+    float fd;
+    if (div != 0.0f) {
+        fd = floorf(div);
+        if (__fsub_rn(div, fd) > 0.5f) fd = __fadd_rn(fd, 1.0f);
+    } else {
+        fd = copysignf(0.0f, __fdiv_rn(a, b));
+    }
+    return fd;
+}
+
+// Query-to-trajectory distance exactly as the oracle / torch evaluate it in float32:
+// l2: fl(fl(dy*dy) + fl(dx*dx)); l1: fl(|dy| + |dx|), dy = gy - py (focus.py:132-135).
+__device__ __forceinline__ float knn_dist(float gy, float gx, float py, float px, int l1)
+{
+    float dy = __fsub_rn(gy, py), dx = __fsub_rn(gx, px);
+    return l1 ? __fadd_rn(fabsf(dy), fabsf(dx))
+              : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+}
+
+__device__ __forceinline__ bool lex_less(float d1, int j1, float d2, int j2)
+{
+    return d1 < d2 || (d1 == d2 && j1 < j2);
+}
+
+// The four bilinear corners of one warped event (event_image_converter.py:354-386).
+struct Corners {
+    int idx[4];      // linear pixel index, -1 when the corner is out of bounds
+    float fy, fx;    // fractional parts (may be slightly negative)
+};
+
+__device__ __forceinline__ Corners vote_corners(float wy, float wx, int H, int W)
+{
+    Corners c;
+    float y1 = floorf(__fadd_rn(wy, kVoteEps));
+    float x1 = floorf(__fadd_rn(wx, kVoteEps));
+    c.fy = __fsub_rn(wy, y1);
+    c.fx = __fsub_rn(wx, x1);
+    // range tests in float so huge / NaN coordinates never reach the int conversion
+    bool y0ok = (y1 >= 0.0f) && (y1 < (float)H);
+    bool y1ok = (y1 >= -1.0f) && (y1 < (float)(H - 1));
+    bool x0ok = (x1 >= 0.0f) && (x1 < (float)W);
+    bool x1ok = (x1 >= -1.0f) && (x1 < (float)(W - 1));
+    int iy = (y0ok || y1ok) ? (int)y1 : 0;
+    int ix = (x0ok || x1ok) ? (int)x1 : 0;
+    c.idx[0] = (y0ok && x0ok) ? iy * W + ix : -1;             // (y1,   x1)
+    c.idx[1] = (y1ok && x0ok) ? (iy + 1) * W + ix : -1;       // (y1+1, x1)
+    c.idx[2] = (y0ok && x1ok) ? iy * W + ix + 1 : -1;         // (y1,   x1+1)
+    c.idx[3] = (y1ok && x1ok) ? (iy + 1) * W + ix + 1 : -1;   // (y1+1, x1+1)
+    return c;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum (fixed tree order -> deterministic); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *smem32)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem32[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < nw ? smem32[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace cmax

@@ -1,0 +1,281 @@
+// event_stage.cu - per-event work of the CMax loss: LUT lookup + warp (upstream
+// src/losses/focus.py:182-195), weights (focus.py:197-214), bilinear vote into the raw IWE
+// (src/utils/event_image_converter.py:333-391) and its adjoint (gather of dL/dIWE at the four
+// corners, reduction into dL/dLUT).
+//
+// One pass over the event stream each way: 24 B read per event row, nothing written per
+// event.  The reference materialises ~25 [B, M]-sized temporaries - here the
+// warped coordinate, weight, corner indices and votes live in registers only.
+// IWE / dLUT accumulation: red.global.add.f32 (L2-resident targets), or int64 fixed point
+// (2^-32) when deterministic.
+#include "cmax_common.cuh"
+
+namespace cmax {
+
+struct EventRow { float y, x, t, p, bin, valid; };
+
+__device__ __forceinline__ EventRow load_event(const float *row)
+{
+    float2 a = ld_stream_f2(row), b = ld_stream_f2(row + 2), c = ld_stream_f2(row + 4);
+    EventRow e{a.x, a.y, b.x, b.y, c.x, c.y};
+    return e;
+}
+
+// LUT cell of an event (focus.py:185-187). Returns false when outside the table.
+__device__ __forceinline__ bool lut_cell(const EventRow &e, const Geom &g, int64_t b, int64_t *cell)
+{
+    float fs = (float)g.s;
+    float fy = floordiv_f32(e.y, fs), fx = floordiv_f32(e.x, fs);
+    float ft = truncf(e.bin);
+    if (!(ft >= 0.0f && ft < (float)g.nb && fy >= 0.0f && fy < (float)g.Hq && fx >= 0.0f &&
+          fx < (float)g.Wq))
+        return false;
+    *cell = ((b * g.nb + (int)ft) * g.Hq + (int)fy) * g.Wq + (int)fx;
+    return true;
+}
+
+// weight of a warped event (focus.py:201-214), no gradient flows through it
+__device__ __forceinline__ float event_weight(const EventRow &e, float wy, float wx, float tref,
+                                              const Geom &g)
+{
+    float w = e.valid;
+    if (g.scale_dt) {
+        float dt = fminf(fmaxf(fabsf(__fsub_rn(e.t, tref)), 0.0f), 1.0f);
+        w = __fmul_rn(__fsub_rn(1.0f, dt), w);
+    }
+    if (g.mask_border) {
+        if (wy > (float)g.H || wx > (float)g.W || wy < 0.0f || wx < 0.0f) w = 0.0f;
+    }
+    return w;
+}
+
+template <bool DET>
+__global__ void __launch_bounds__(256)
+event_forward_kernel(const float *__restrict__ events, const float *__restrict__ times, Geom g,
+                     const float *__restrict__ lut, float *__restrict__ raw,
+                     long long *__restrict__ raw_i64, long long *__restrict__ status)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (m >= g.M) return;
+    const EventRow e = load_event(events + (b * g.M + m) * 6);
+    if (e.valid == 0.0f) return;                      // padding rows vote 0 everywhere
+    int64_t cell;
+    if (!lut_cell(e, g, b, &cell)) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(status), 1ull);
+        return;
+    }
+    const int pol = (g.pab && m >= g.npos) ? 1 : 0;
+    const int64_t HW = (int64_t)g.H * g.W;
+    for (int r = 0; r < g.R; ++r) {
+        const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
+        const float wy = __fadd_rn(f.x, e.y), wx = __fadd_rn(f.y, e.x);     // focus.py:191
+        const float w = event_weight(e, wy, wx, __ldg(times + r), g);
+        if (w == 0.0f) continue;
+        const Corners c = vote_corners(wy, wx, g.H, g.W);
+        const float oy = __fsub_rn(1.0f, c.fy), ox = __fsub_rn(1.0f, c.fx);
+        float v[4];
+        v[0] = __fmul_rn(__fmul_rn(oy, ox), w);        // event_image_converter.py:382-385
+        v[1] = __fmul_rn(__fmul_rn(c.fy, ox), w);
+        v[2] = __fmul_rn(__fmul_rn(oy, c.fx), w);
+        v[3] = __fmul_rn(__fmul_rn(c.fy, c.fx), w);
+        const int64_t base = ((b * g.R + r) * g.P + pol) * HW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c.idx[k] >= 0) {
+                if (DET)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + c.idx[k]),
+                              (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                else
+                    atomicAdd(raw + base + c.idx[k], v[k]);
+            }
+        }
+    }
+}
+
+// int64 fixed point -> float image
+__global__ void fix_to_float_kernel(const long long *__restrict__ in, float *__restrict__ out,
+                                    int64_t count)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (float)((double)in[i] * (1.0 / kFixScale));
+}
+
+// Backward: g' = w * (d vote / d (wy, wx)) . D   with D = *unscaled* dL/dIWE at the corners;
+// dLUT[cell, r] += coef * g'   where coef = grad_loss * (-1 / val^2) / N  (loss.py:12,22-25).
+template <bool DET>
+__global__ void __launch_bounds__(256)
+event_backward_kernel(const float *__restrict__ events, const float *__restrict__ times, Geom g,
+                      const float *__restrict__ lut, const float *__restrict__ dimg,
+                      const Header *__restrict__ hdr, const float *__restrict__ grad_loss,
+                      float *__restrict__ dlut, long long *__restrict__ dlut_i64)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (m >= g.M) return;
+    const EventRow e = load_event(events + (b * g.M + m) * 6);
+    if (e.valid == 0.0f) return;
+    int64_t cell;
+    if (!lut_cell(e, g, b, &cell)) return;
+    const int pol = (g.pab && m >= g.npos) ? 1 : 0;
+    const int64_t HW = (int64_t)g.H * g.W;
+    float coef = 1.0f;
+    if (!DET) {
+        const float val = hdr->val;
+        const float N = (float)((double)g.B * g.R * g.P * (double)HW);
+        coef = __ldg(grad_loss) * (-(1.0f / (val * val))) / N;
+    }
+    for (int r = 0; r < g.R; ++r) {
+        const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
+        const float wy = __fadd_rn(f.x, e.y), wx = __fadd_rn(f.y, e.x);
+        const float w = event_weight(e, wy, wx, __ldg(times + r), g);
+        if (w == 0.0f) continue;
+        const Corners c = vote_corners(wy, wx, g.H, g.W);
+        const float *D = dimg + ((b * g.R + r) * g.P + pol) * HW;
+        const float d00 = c.idx[0] >= 0 ? __ldg(D + c.idx[0]) : 0.0f;
+        const float d10 = c.idx[1] >= 0 ? __ldg(D + c.idx[1]) : 0.0f;
+        const float d01 = c.idx[2] >= 0 ? __ldg(D + c.idx[2]) : 0.0f;
+        const float d11 = c.idx[3] >= 0 ? __ldg(D + c.idx[3]) : 0.0f;
+        const float oy = 1.0f - c.fy, ox = 1.0f - c.fx;
+        const float gy = w * (ox * (d10 - d00) + c.fx * (d11 - d01));
+        const float gx = w * (oy * (d01 - d00) + c.fy * (d11 - d10));
+        if (DET) {
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
+            atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
+            atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
+        } else {
+            float *dst = dlut + (cell * g.R + r) * 2;
+            atomicAdd(dst, coef * gy);
+            atomicAdd(dst + 1, coef * gx);
+        }
+    }
+}
+
+// deterministic mode: dLUT = coef * fixed-point sum (+ the smoothness gradient already there)
+__global__ void dlut_finalize_kernel(const long long *__restrict__ acc, float *__restrict__ dlut,
+                                     const Header *__restrict__ hdr,
+                                     const float *__restrict__ grad_loss, double N, int64_t count)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float val = hdr->val;
+    const float coef = __ldg(grad_loss) * (-(1.0f / (val * val))) / (float)N;
+    dlut[i] += coef * (float)((double)acc[i] * (1.0 / kFixScale));
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone imager kernels (cmax_create_iwe / cmax_count_image)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>   // 0: float votes, 1: int64 fixed-point votes, 2: unit counts (int64)
+__global__ void __launch_bounds__(256)
+splat_kernel(const float *__restrict__ events, const float *__restrict__ weight, int64_t M,
+             int64_t stride, int H, int W, float *__restrict__ out, long long *__restrict__ out_i64)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (m >= M) return;
+    const float *row = events + (b * M + m) * stride;
+    const float wy = row[0], wx = row[1];
+    const float w = weight ? weight[b * M + m] : 1.0f;
+    const Corners c = vote_corners(wy, wx, H, W);
+    const int64_t base = b * (int64_t)H * W;
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c.idx[k] >= 0)
+                atomicAdd(reinterpret_cast<unsigned long long *>(out_i64 + base + c.idx[k]), 1ull);
+        return;
+    }
+    const float oy = __fsub_rn(1.0f, c.fy), ox = __fsub_rn(1.0f, c.fx);
+    float v[4];
+    v[0] = __fmul_rn(__fmul_rn(oy, ox), w);
+    v[1] = __fmul_rn(__fmul_rn(c.fy, ox), w);
+    v[2] = __fmul_rn(__fmul_rn(oy, c.fx), w);
+    v[3] = __fmul_rn(__fmul_rn(c.fy, c.fx), w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c.idx[k] >= 0) {
+            if (MODE == 1)
+                atomicAdd(reinterpret_cast<unsigned long long *>(out_i64 + base + c.idx[k]),
+                          (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+            else
+                atomicAdd(out + base + c.idx[k], v[k]);
+        }
+    }
+}
+
+int launch_splat(int mode, const float *events, const float *weight, int64_t nb, int64_t M,
+                 int64_t stride, int H, int W, float *out, long long *out_i64, cudaStream_t st)
+{
+    if (M == 0 || nb == 0) return CMAX_OK;
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)nb);
+    if (mode == 0)
+        splat_kernel<0><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+    else if (mode == 1)
+        splat_kernel<1><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+    else
+        splat_kernel<2><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+    return check_launch();
+}
+
+int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStream_t st)
+{
+    if (count == 0) return CMAX_OK;
+    fix_to_float_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(in, out, count);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int launch_event_forward(const Geom &g, const Layout &L, const float *events, const float *times,
+                         char *ws, cudaStream_t st)
+{
+    const int64_t count = g.B * g.R * g.P * (int64_t)g.H * g.W;
+    float *raw = reinterpret_cast<float *>(ws + L.raw);
+    long long *raw_i64 = reinterpret_cast<long long *>(ws + L.raw_i64);
+    long long *status = reinterpret_cast<Header *>(ws + L.header)->status;
+    const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    if (g.det)
+        cudaMemsetAsync(raw_i64, 0, sizeof(long long) * count, st);
+    else
+        cudaMemsetAsync(raw, 0, sizeof(float) * count, st);
+    if (g.M > 0) {
+        dim3 grid((unsigned)((g.M + 255) / 256), (unsigned)g.B);
+        if (g.det)
+            event_forward_kernel<true><<<grid, 256, 0, st>>>(events, times, g, lut, raw, raw_i64, status);
+        else
+            event_forward_kernel<false><<<grid, 256, 0, st>>>(events, times, g, lut, raw, raw_i64, status);
+    }
+    if (g.det) return launch_fix_to_float(raw_i64, raw, count, st);
+    return check_launch();
+}
+
+int launch_event_backward(const Geom &g, const Layout &L, const float *events, const float *times,
+                          const float *grad_loss, char *ws, cudaStream_t st)
+{
+    const int64_t count = g.S * g.q * g.R * 2;
+    const Header *hdr = reinterpret_cast<const Header *>(ws + L.header);
+    const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    const float *dimg = reinterpret_cast<const float *>(ws + L.dimg);
+    float *dlut = reinterpret_cast<float *>(ws + L.dlut);
+    long long *dlut_i64 = reinterpret_cast<long long *>(ws + L.dlut_i64);
+    if (g.det) cudaMemsetAsync(dlut_i64, 0, sizeof(long long) * count, st);
+    if (g.M > 0) {
+        dim3 grid((unsigned)((g.M + 255) / 256), (unsigned)g.B);
+        if (g.det)
+            event_backward_kernel<true><<<grid, 256, 0, st>>>(events, times, g, lut, dimg, hdr,
+                                                               grad_loss, dlut, dlut_i64);
+        else
+            event_backward_kernel<false><<<grid, 256, 0, st>>>(events, times, g, lut, dimg, hdr,
+                                                                grad_loss, dlut, dlut_i64);
+    }
+    if (g.det) {
+        const double N = (double)g.B * g.R * g.P * (double)g.H * g.W;
+        dlut_finalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dlut_i64, dlut, hdr,
+                                                                             grad_loss, N, count);
+    }
+    return check_launch();
+}
+
+}  // namespace cmax

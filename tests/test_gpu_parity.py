@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden vectors
+and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): bit-exact for integer work (corner indices / masks /
+count image / KNN neighbour sets); 1e-5 relative (norm-wise) on loss, IWE, LUT and gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import LOSS_CASES, GOLDEN_DIR, load_case, rel_err, max_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _cuda():
+    assert torch.cuda.is_available(), "these tests need a GPU (run with -m gpu on a B200)"
+    return torch.device("cuda:0")
+
+
+def _run_loss(cfg, traj, times, events, npos, deterministic=False, grad_scale=1.0):
+    from motionpriorcmax_b200.losses import LossFactory
+    dev = _cuda()
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=deterministic))
+    t = torch.as_tensor(traj, device=dev).clone().requires_grad_()
+    batch = {"events": torch.as_tensor(events, device=dev)}
+    if npos >= 0:
+        batch["num_pos_events"] = npos
+    loss, log, misc = L.calc(t, torch.as_tensor(times, device=dev), batch, return_flow_lut=True)
+    (loss * grad_scale).backward()
+    torch.cuda.synchronize()
+    return dict(loss=loss.item(), focus=log["focus_loss"].item(), smooth=log["smoothness_loss"].item(),
+                iwes=misc["iwes"].cpu().numpy(), lut=misc["flow_lut"].cpu().numpy(),
+                dtraj=t.grad.cpu().numpy(), loss_t=loss)
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors of the real reference
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", LOSS_CASES)
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_loss_matches_reference_golden(name, deterministic):
+    c = load_case(name)
+    r = _run_loss(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"],
+                  deterministic)
+    assert abs(r["loss"] - float(c["loss"])) <= TOL * abs(float(c["loss"]))
+    assert abs(r["focus"] - float(c["focus_loss"])) <= TOL * abs(float(c["focus_loss"]))
+    assert abs(r["smooth"] - float(c["smoothness_loss"])) <= TOL * max(abs(float(c["smoothness_loss"])), 1e-3)
+    assert r["iwes"].shape == c["iwes"].shape
+    assert rel_err(r["iwes"], c["iwes"]) < TOL
+    assert r["lut"].shape == c["flow_lut"].shape
+    assert rel_err(r["lut"], c["flow_lut"]) < TOL
+    assert r["dtraj"].shape == c["dtraj"].shape
+    assert rel_err(r["dtraj"], c["dtraj"]) < TOL
+
+
+def test_imager_matches_reference_golden():
+    from motionpriorcmax_b200.utils import EventImageConverter
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    z = np.load(f"{GOLDEN_DIR}/imager.npz")
+    H, W = (int(v) for v in z["shape"])
+    ev = torch.as_tensor(z["events"], device=dev)
+    wt = torch.as_tensor(z["weight"], device=dev)
+    for det in (False, True):
+        im = EventImageConverter((H, W), deterministic=det)
+        a = im.create_iwe(ev, method="bilinear_vote", sigma=1, weight=wt).cpu().numpy()
+        assert a.shape == z["iwe_sigma1"].shape and rel_err(a, z["iwe_sigma1"]) < TOL
+        b = im.create_iwe(ev, method="bilinear_vote", sigma=0, weight=wt).cpu().numpy()
+        assert b.shape == z["iwe_sigma0"].shape and rel_err(b, z["iwe_sigma0"]) < TOL
+        u = im.create_iwe(ev, method="bilinear_vote", sigma=0).cpu().numpy()
+        assert rel_err(u, z["iwe_unit"]) < TOL
+    # integer work: count image bit-exact against the oracle's restatement of the shared
+    # index / mask arithmetic (the reference's own count_event_tensor raises, see make_golden.py)
+    cnt = EventImageConverter((H, W)).create_image_from_events_tensor(ev, method="count").cpu().numpy()
+    assert cnt.dtype == np.int64
+    assert np.array_equal(cnt, fo.count_image(z["events"], (H, W)))
+
+
+# ------------------------------------------------------------------------------------------
+# integer work: bit exact
+# ------------------------------------------------------------------------------------------
+def test_count_image_bit_exact_on_adversarial_coordinates():
+    from motionpriorcmax_b200.utils import EventImageConverter
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    rng = np.random.default_rng(3)
+    H, W = 37, 53
+    n = 200_000
+    yx = (rng.random((3, n, 2)) * [H + 4, W + 4] - 2).astype(np.float32)
+    # values within a few ulp of integers on both sides, where floor(v + 1e-6f) is decided in fp32
+    k = n // 4
+    base = rng.integers(-1, max(H, W) + 1, (3, k, 2)).astype(np.float32)
+    yx[:, :k] = base + rng.choice(np.array([-2e-6, -1e-6, -5e-7, -1e-7, 0, 1e-7, 1e-6], np.float32), (3, k, 2))
+    ev = np.concatenate((yx, np.zeros((3, n, 2), np.float32)), -1)
+    got = EventImageConverter((H, W)).count_event_tensor(torch.as_tensor(ev, device=dev)).cpu().numpy()
+    assert np.array_equal(got, fo.count_image(ev, (H, W)))
+    # deterministic float IWE with unit weights on integer coordinates equals the count image
+    ev_int = ev.copy()
+    ev_int[..., :2] = np.floor(ev_int[..., :2])
+    im = EventImageConverter((H, W), deterministic=True)
+    unit = im.create_iwe(torch.as_tensor(ev_int, device=dev), sigma=0).cpu().numpy()
+    cnt = fo.count_image(ev_int, (H, W))
+    _, mask, frac = fo.vote_corners(ev_int[..., :2], (H, W))
+    # integer coordinates: all weight on corner 0
+    ref = np.zeros_like(cnt)
+    inds, mask, _ = fo.vote_corners(ev_int[..., :2], (H, W))
+    for b in range(3):
+        ref[b] = np.bincount(inds[b, :, 0], weights=mask[b, :, 0].astype(np.float64),
+                             minlength=H * W).reshape(H, W).astype(np.int64)
+    assert np.array_equal(unit.astype(np.int64), ref)
+
+
+@pytest.mark.parametrize("norm", ["l2", "l1"])
+@pytest.mark.parametrize("shape,s,n,K", [((32, 48), 4, 96, 8), ((40, 56), 4, 333, 12),
+                                         ((64, 96), 4, 384, 32), ((48, 64), 8, 1000, 5),
+                                         ((30, 45), 3, 50, 50), ((64, 64), 2, 5000, 1)])
+def test_knn_neighbour_sets_bit_exact(norm, shape, s, n, K):
+    from motionpriorcmax_b200 import cabi
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    lib = cabi.load()
+    H, W = shape
+    rng = np.random.default_rng(n + K)
+    S = 3
+    pts = (rng.random((1, S, n, 2)) * [H + 20, W + 20] - 10).astype(np.float32)
+    pts[0, 1, : n // 3] = np.round(pts[0, 1, : n // 3])          # exact ties
+    pts[0, 2] = pts[0, 2] * 0.3 + np.array([H / 2, W / 2], np.float32)   # dense cluster, empty rim
+    grid, Hq, Wq = fo.lut_grid(shape, s)
+    ind_ref, dist_ref = fo.knn_bruteforce(pts, grid, K, norm)
+    p = torch.as_tensor(pts[0], device=dev).contiguous()
+    ind = torch.empty((S, Hq * Wq, K), dtype=torch.int32, device=dev)
+    dist = torch.empty((S, Hq * Wq, K), dtype=torch.float32, device=dev)
+    need = lib.cmax_knn_workspace_bytes(H, W, s, S, n, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    rc = lib.cmax_knn_indices(cabi.ptr(p), S, n, H, W, s, K, cabi.NORM[norm], cabi.ptr(ind),
+                              cabi.ptr(dist), cabi.ptr(ws), need, cabi.stream_ptr(dev))
+    cabi.check(rc, "cmax_knn_indices")
+    torch.cuda.synchronize()
+    assert np.array_equal(ind.cpu().numpy().astype(np.int64), ind_ref[0])
+    assert np.array_equal(dist.cpu().numpy(), dist_ref[0])
+
+
+def test_zero_flow_lattice_ties():
+    """All-zero flow: trajectories sit on the tile lattice, every query has 4-way ties."""
+    from oracle import focus_oracle as fo
+    cfg = dict(load_case("dsec_like_pab")["cfg"])
+    c = load_case("dsec_like_pab")
+    H, W = cfg["image_shape"]
+    pos = fo.tile_positions((H, W), 4).astype(np.float32)
+    n_t = cfg["num_tref"] + cfg["num_bins"]
+    traj = np.broadcast_to(pos[None, None], (2, n_t, len(pos), 2)).copy()
+    r = _run_loss(cfg, traj, c["times"], c["events"], c["num_pos_events"])
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, c["times"], c["events"], c["num_pos_events"])
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert np.abs(r["lut"]).max() == 0.0
+    assert rel_err(r["dtraj"], g["dtraj"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------
+# oracle comparisons on seeded mid-size inputs (float64 oracle = truth)
+# ------------------------------------------------------------------------------------------
+def _synthetic_case(cfg, B, M, K_basis, seed, dist="uniform", basis="polynomial"):
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    H, W = cfg["image_shape"]
+    times = fo.reconstruction_times(cfg["num_tref"], cfg["num_bins"], 0.43)
+    cg = synthetic.make_coeff_grid(B, K_basis, H, W, sigma_px=6.0, seed=seed, coarse=(5, 6)).numpy()
+    traj, _ = fo.trajectories_from_coeff_grid(cg, times, 4, K_basis, basis)
+    ev, npos = synthetic.make_event_batch(B, M, H, W, cfg["num_bins"], cfg["polarity_aware_batching"],
+                                          seed=seed, dist=dist)
+    return traj, times, ev.numpy(), (-1 if npos is None else npos), cg
+
+
+@pytest.mark.parametrize("variant", ["dsec", "dsec_l2", "multi_tref5", "evimo_next", "iwd_l1"])
+def test_loss_matches_oracle_midsize(variant):
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    base = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(96, 128), num_knn=16)
+    if variant == "dsec_l2":
+        base.update(focus_loss_norm="l2")
+    elif variant == "multi_tref5":
+        base = synthetic.multi_tref_variant(base, 5)
+    elif variant == "evimo_next":
+        base.update(smooth_type="on_flow_to_next", smooth_weight=0.06, num_bins=9)
+    elif variant == "iwd_l1":
+        base.update(interpolation_scheme="iwd", dist_norm="l1")
+    traj, times, ev, npos, _ = _synthetic_case(base, 3, [20000, 35000, 9000], 2, seed=11,
+                                               dist="edges" if variant == "dsec" else "uniform")
+    r = _run_loss(base, traj, times, ev, npos)
+    o = fo.FocusOracle(**base, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert abs(r["focus"] - f["focus_loss"]) <= TOL * abs(f["focus_loss"])
+    assert abs(r["smooth"] - f["smoothness_loss"]) <= TOL * max(abs(f["smoothness_loss"]), 1e-3)
+    assert rel_err(r["iwes"], f["iwes"]) < TOL
+    assert rel_err(r["lut"], f["flow_lut"]) < TOL
+    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL     # l1 sign() flips on ~0 Sobel responses
+
+
+def test_deterministic_mode_is_bit_reproducible_and_close():
+    from motionpriorcmax_b200 import synthetic
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(96, 128), num_knn=16)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 60000, 3, seed=5, dist="edges")
+    a = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    b = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    for k in ("iwes", "lut", "dtraj"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["loss"] == b["loss"]
+    c = _run_loss(cfg, traj, times, ev, npos, deterministic=False)
+    assert abs(a["loss"] - c["loss"]) <= TOL * abs(c["loss"])
+    assert rel_err(a["iwes"], c["iwes"]) < TOL and rel_err(a["dtraj"], c["dtraj"]) < TOL
+
+
+def test_gradient_against_finite_differences():
+    """Directional derivative of the (l2-norm, hence smooth) loss vs central differences of the
+    float64 oracle - checks the whole hand-written backward chain end to end."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(48, 64), num_knn=6, focus_loss_norm="l2",
+               num_bins=5)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 8000, 1, seed=2)
+    r = _run_loss(cfg, traj, times, ev, npos)
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal(traj.shape)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    ind = o.forward(traj, times, ev, npos)["ind_k"]
+    eps = 1e-4
+
+    def lossd(t):
+        return float(fo.FocusOracle(**cfg, dtype=np.float64).forward(
+            t.astype(np.float32), times, ev, npos, ind_k=ind)["loss"])
+    # float32 rounding of the perturbed trajectories limits the accuracy of the quotient
+    fd = (lossd(traj + eps * d) - lossd(traj - eps * d)) / (2 * eps)
+    an = float((r["dtraj"].astype(np.float64) * d).sum())
+    assert abs(fd - an) <= 2e-2 * max(abs(fd), 1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size DSEC window (config[0] of BASELINE.json) against the oracle + properties
+# ------------------------------------------------------------------------------------------
+def test_full_size_dsec_window_matches_oracle():
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 1, 300_000, 1, seed=1234)
+    r = _run_loss(cfg, traj, times, ev, npos)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["iwes"], f["iwes"]) < TOL
+    assert rel_err(r["lut"], f["flow_lut"]) < TOL
+    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+
+
+def test_properties_at_full_size():
+    """Size-independent properties on a DSEC-shaped batch the oracle could not finish quickly:
+    padding rows are inert, the gradient is linear in grad_loss, event order inside a polarity
+    group does not matter, mass conservation of the raw vote."""
+    from motionpriorcmax_b200 import synthetic
+    from motionpriorcmax_b200.utils import EventImageConverter
+    dev = _cuda()
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, mask_image_border=False, scale_iwe_by_dt=False)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, [400_000, 250_000], 1, seed=77)
+    a = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    # (1) linear in grad_loss
+    b = _run_loss(cfg, traj, times, ev, npos, deterministic=True, grad_scale=3.0)
+    assert rel_err(b["dtraj"], 3.0 * a["dtraj"]) < 1e-6
+    # (2) permuting the events inside the positive group changes nothing (deterministic mode)
+    ev2 = ev.copy()
+    perm = np.random.default_rng(0).permutation(npos)
+    ev2[:, :npos] = ev[:, :npos][:, perm]
+    c = _run_loss(cfg, traj, times, ev2, npos, deterministic=True)
+    assert np.array_equal(a["iwes"], c["iwes"]) and a["loss"] == c["loss"]
+    # (3) extra padding rows (valid = 0) are inert
+    ev3 = np.concatenate((ev, np.zeros((2, 1000, 6), np.float32)), 1)
+    d = _run_loss(cfg, traj, times, ev3, npos, deterministic=True)
+    assert np.array_equal(a["iwes"], d["iwes"]) and np.array_equal(a["dtraj"], d["dtraj"])
+    # (4) mass conservation: every in-bounds vote sums to the event weight
+    H, W = cfg["image_shape"]
+    inner = ev[0, ev[0, :, 5] > 0][:, :2].copy()
+    inner = inner[(inner[:, 0] < H - 1) & (inner[:, 1] < W - 1)]
+    raw = EventImageConverter((H, W), deterministic=True).create_iwe(
+        torch.as_tensor(inner, device=dev), sigma=0)
+    assert abs(raw.double().sum().item() - len(inner)) < 1e-3 * len(inner) ** 0.5
+
+
+def test_edge_cases_empty_and_tiny():
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(32, 48), num_knn=4, num_bins=3)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 50, 1, seed=9)
+    # one sample entirely padding
+    ev[1] = 0
+    r = _run_loss(cfg, traj, times, ev, npos)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+    # K == n (every trajectory is a neighbour of every cell)
+    cfg2 = dict(cfg, num_knn=traj.shape[2])
+    r2 = _run_loss(cfg2, traj, times, ev, npos)
+    f2 = fo.FocusOracle(**cfg2, dtype=np.float64).forward(traj, times, ev, npos)
+    assert abs(r2["loss"] - f2["loss"]) <= TOL * abs(f2["loss"])
+    assert rel_err(r2["lut"], f2["flow_lut"]) < TOL
+
+
+def test_error_behaviour_mirrors_reference():
+    from motionpriorcmax_b200.losses import LossFactory
+    from motionpriorcmax_b200 import synthetic
+    with pytest.raises(ValueError):
+        LossFactory.get_loss_calculator("NOPE", {})
+    with pytest.raises(AssertionError):
+        LossFactory.get_loss_calculator("FOCUS", dict(synthetic.DSEC_LOSS_CONFIG, num_tref=3))
+    L = LossFactory.get_loss_calculator("FOCUS", dict(synthetic.DSEC_LOSS_CONFIG))
+    dev = _cuda()
+    with pytest.raises(AssertionError):          # focus.py:80: pab needs num_pos_events
+        L.calc(torch.zeros(1, 16, 19200, 2, device=dev), torch.zeros(16, device=dev),
+               {"events": torch.zeros(1, 10, 6, device=dev)})
+    with pytest.raises(RuntimeError):            # no CPU fallback
+        L.calc(torch.zeros(1, 16, 19200, 2), torch.zeros(16), {"events": torch.zeros(1, 10, 6),
+                                                                "num_pos_events": 5})
+
+
+def test_front_end_matches_oracle_and_golden():
+    from motionpriorcmax_b200 import trajectories as tj
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    for name in LOSS_CASES:
+        c = load_case(name)
+        if "coeff_grid" not in c:
+            continue
+        basis, K, patch = str(c["basis"]), int(c["num_basis"]), int(c["patch"])
+        cg = torch.as_tensor(c["coeff_grid"], device=dev).requires_grad_()
+        times = torch.as_tensor(c["times"], device=dev)
+        tr = tj.calculate_trajectories_at_t(cg, times, patch, K, basis)
+        assert rel_err(tr.detach().cpu().numpy(), c["trajectories"]) < 1e-6
+        gout = torch.randn_like(tr)
+        tr.backward(gout)
+        ref = fo.trajectories_backward(gout.cpu().numpy(), c["times"], patch, K, basis,
+                                       c["coeff_grid"].shape)
+        assert rel_err(cg.grad.cpu().numpy(), ref) < 1e-5
