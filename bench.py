@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py - CMax loss forward+backward throughput (events/s) on B200, per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--events M] [--batch B] [--variant dsec|dsec_tref5|evimo2|k3_det] [--sweep]
+
+One "step" = one pass of the loss hot path over one batch of synthetic event windows:
+coeff_grid -> trajectories (fused front end) -> FocusLoss.calc -> backward to d coeff_grid.
+Default workload = BASELINE.json configs[1]: DSEC training shape, per-rank batch 14, 480x640,
+15 bins, K_nn 32, poly k=1, polarity-aware, as-shipped dsec.yaml loss block, event counts
+~LogNormal(1e6, 0.5) per window.
+
+Printed JSON line (rank 0): see the keys below; `value` = valid events of all ranks per second
+with inputs resident in HBM (CUDA events, max over ranks); `e2e` = same metric through the
+plugin API with pinned HOST inputs copied in (double-buffered) and the loss read back, every
+step inside the timed region; `roofline` = dominant kernel (by measured stage time) against
+the HBM peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port timed on the host
+cores on a bounded sample (one window).
+
+`--impl reference` times the reference's algorithm on the CPU (the oracle port: the reference
+is Python + pykeops and cannot run on the box) on the same config and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------
+# workload definitions
+# ------------------------------------------------------------------------------------------
+def workload(variant: str, batch: int | None, events: int | None):
+    from motionpriorcmax_b200 import synthetic
+    if variant == "dsec":
+        cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+        w = dict(name="dsec_train_b14_480x640_polyk1_pab", B=batch or 14, K=1, basis="polynomial",
+                 median=events or 1_000_000, lognormal=events is None, deterministic=False)
+    elif variant == "dsec_tref5":
+        cfg = synthetic.multi_tref_variant(synthetic.DSEC_LOSS_CONFIG, 5)
+        w = dict(name="dsec_train_b14_480x640_polyk1_tref5", B=batch or 14, K=1, basis="polynomial",
+                 median=events or 1_000_000, lognormal=events is None, deterministic=False)
+    elif variant == "evimo2":
+        cfg = dict(synthetic.EVIMO2_LOSS_CONFIG)
+        w = dict(name="evimo2_300ms_b6_384x512_bezier10", B=batch or 6, K=10, basis="bezier",
+                 median=events or 1_000_000, lognormal=False, deterministic=False, integer=True)
+    elif variant == "k3_det":
+        cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+        w = dict(name="dsec_k3_5Mevents_deterministic", B=batch or 1, K=3, basis="polynomial",
+                 median=events or 5_000_000, lognormal=False, deterministic=True)
+    else:
+        raise ValueError(variant)
+    return cfg, w
+
+
+def make_inputs(cfg, w, rank: int):
+    """CPU tensors of one batch: coeff_grid [B,1,2K,H,W], events [B,M,6], num_pos, times."""
+    from motionpriorcmax_b200 import synthetic
+    H, W = cfg["image_shape"]
+    B = w["B"]
+    if w["lognormal"]:
+        counts = synthetic.lognormal_event_counts(B, median=w["median"], rank=rank)
+    else:
+        counts = [int(w["median"])] * B
+    ev, npos = synthetic.make_event_batch(B, counts, H, W, cfg["num_bins"],
+                                          cfg["polarity_aware_batching"], seed=1234, rank=rank,
+                                          integer_coords=w.get("integer", False), coord_scale=0.8)
+    cg = synthetic.make_coeff_grid(B, w["K"], H, W, sigma_px=8.0, seed=1234 + 1000 * rank)
+    n_valid = int(ev[..., 5].sum().item())
+    return cg, ev, npos, n_valid
+
+
+def algorithmic_bytes(cfg, w, B, M, n, include_knn_idx=False):
+    """bytes_alg = 48 E + 20 B R P H W + 24 B Q R + 16 B n_t n."""
+    H, W = cfg["image_shape"]
+    R, nb, s = cfg["num_tref"], cfg["num_bins"], cfg["lut_superpixel_size"]
+    P = 2 if cfg["polarity_aware_batching"] else 1
+    Q = nb * math.ceil(H / s) * math.ceil(W / s)
+    return dict(events=48 * B * M, image=20 * B * R * P * H * W, lut=24 * B * Q * R,
+                traj=16 * B * (R + nb) * n)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (pynvml; nvidia-smi fallback)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clocks"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name not in ("gpu_idle",):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle port)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=1):
+    """One loss forward+backward of the CPU oracle on the first `sample_windows` windows.
+    Returns (seconds, valid events processed)."""
+    from oracle import focus_oracle as fo
+    B = min(sample_windows, ev.shape[0])
+    evs = ev[:B].numpy()
+    times = fo.reconstruction_times(cfg["num_tref"], cfg["num_bins"], 0.5)
+    t0 = time.perf_counter()
+    traj, _ = fo.trajectories_from_coeff_grid(cg[:B].numpy(), times, 4, w["K"], w["basis"])
+    o = fo.FocusOracle(**cfg, dtype=np.float32)
+    o.forward(traj, times, evs, -1 if npos is None else npos)
+    g = o.backward()
+    fo.trajectories_backward(g["dtraj"], times, 4, w["K"], w["basis"], tuple(cg[:B].shape),
+                             dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return dt, int(evs[..., 5].sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, w = workload(args.variant, args.batch, args.events)
+    cg, ev, npos, _ = make_inputs(cfg, dict(w, B=1), 0)         # bounded sample: one window
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_step(cfg, w, cg, ev, npos)
+    secs, n_ev = [], 0
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        dt, n_ev = cpu_reference_step(cfg, w, cg, ev, npos)
+        secs.append(dt)
+    t = statistics.median(secs)
+    val = n_ev / t
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "cmax_loss_fwd_bwd_events_per_sec", "value": val,
+        "unit": "events/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": "1 window of the batch per step",
+                   "events_per_step": n_ev},
+        "cpu_baseline": {"value": val, "unit": "events/s", "cores": cores, "kind": "port",
+                         "sample": f"1 window ({n_ev} events) fwd+bwd, oracle port of the reference "
+                                   f"loss (numpy event stage 1 thread + C/OpenMP exhaustive KNN on "
+                                   f"{cores} threads); the Python+pykeops reference cannot run on the box"},
+        "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    from motionpriorcmax_b200 import cabi, trajectories as tj
+    from motionpriorcmax_b200.losses import LossFactory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cabi.load()
+
+    cfg, w = workload(args.variant, args.batch, args.events)
+    H, W = cfg["image_shape"]
+    cg_h, ev_h, npos, n_valid = make_inputs(cfg, w, rank)
+    B, M = ev_h.shape[0], ev_h.shape[1]
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=w["deterministic"]))
+    times = L.get_reconstruction_times(dev)
+    if cfg["num_tref"] == 1:
+        times[0] = 0.5
+    batch_keys = {} if npos is None else {"num_pos_events": npos}
+
+    def step(cg_d, ev_d):
+        cg_d.grad = None
+        traj = tj.calculate_trajectories_at_t(cg_d, times, 4, w["K"], w["basis"])
+        loss, _, _ = L.calc(traj, times, dict(batch_keys, events=ev_d))
+        loss.backward()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----------------------------------------------------------------
+    cg_d = cg_h.to(dev).requires_grad_()
+    ev_d = ev_h.to(dev)
+    n_traj = tj.tile_positions((H, W), 4).shape[0]
+    for _ in range(args.prof_warmup if args.prof_warmup is not None else max(3, args.warmup)):
+        step(cg_d, ev_d)
+    barrier()
+    launches0 = lib.cmax_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.cmax_stage_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(cg_d, ev_d)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    stage = cabi.stage_timing_read()
+    lib.cmax_stage_timing_enable(0)
+    launches = lib.cmax_launch_count() - launches0
+
+    # ---- end-to-end arm: pinned host inputs, double-buffered H2D, loss read back ---------------
+    ev_p, cg_p = ev_h.pin_memory(), cg_h.pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [(torch.empty_like(ev_d), torch.empty_like(cg_d.detach())) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[i])
+            bufs[i][0].copy_(ev_p, non_blocking=True)
+            bufs[i][1].copy_(cg_p, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e_loop(k):
+        cur = torch.cuda.current_stream(dev)
+        for i in range(2):
+            done[i].record(cur)
+        prefetch(0)
+        out = 0.0
+        for it in range(k):
+            i = it & 1
+            if it + 1 < k:
+                prefetch(i ^ 1)
+            cur.wait_event(ready[i])
+            loss = step(bufs[i][1].requires_grad_(), bufs[i][0])
+            done[i].record(cur)
+            out = loss.item()                       # D2H read of the step's result
+            bufs[i][1].requires_grad_(False)
+        return out
+
+    ms_e2e = float("nan")
+    if not args.no_e2e:
+        e2e_loop(2)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_loop(args.steps)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop()
+
+    # ---- max over ranks -----------------------------------------------------------------------
+    t = torch.tensor([ms_total, ms_e2e, float(n_valid), float(B * M)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, ms_e2e = tmax[0].item(), tmax[1].item()
+        ev_all, rows_all = tsum[2].item(), tsum[3].item()
+    else:
+        ev_all, rows_all = float(n_valid), float(B * M)
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = ev_all / (ms_step * 1e-3)
+        e2e_val = ev_all / (ms_e2e / args.steps * 1e-3)
+        # dominant kernel by measured stage time (this rank)
+        per_launch = {k: (v[0] / v[1]) for k, v in stage.items() if v[1] > 0}
+        dom = max(per_launch, key=per_launch.get)
+        ab = algorithmic_bytes(cfg, w, B, M, n_traj)
+        stage_bytes = {
+            "event_forward": ab["events"] / 2, "event_backward": ab["events"] / 2,
+            "image_forward": ab["image"] * 12 / 20, "image_backward": ab["image"] * 8 / 20,
+            "knn_select": ab["lut"] / 3 + ab["traj"] / 2, "lut_backward": ab["lut"] / 3 + ab["traj"] / 2,
+            "smooth_forward": ab["lut"] / 3, "smooth_backward": 2 * ab["lut"] / 3,
+            "bin_points": ab["traj"] / 2,
+        }
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom_bytes = stage_bytes.get(dom, 0.0)
+        achieved = dom_bytes / (per_launch[dom] * 1e-3) / 1e9
+        total_bytes = sum(ab.values())
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        line = {
+            "metric": "cmax_loss_fwd_bwd_events_per_sec", "value": value, "unit": "events/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "per_rank_batch": B, "event_rows_per_window": M,
+                       "events_per_step_all_ranks": ev_all, "event_rows_per_step_all_ranks": rows_all,
+                       "image": [H, W], "num_bins": cfg["num_bins"], "num_tref": cfg["num_tref"],
+                       "num_knn": cfg["num_knn"], "trajectories": n_traj, "basis": w["basis"],
+                       "basis_order": w["K"], "deterministic": w["deterministic"],
+                       "l2_policy": "inputs larger than L2 (events %.0f MB per rank)" % (B * M * 24 / 1e6),
+                       "parallelism": f"dp{world} (windows sharded, no collective in the loss)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "whole_step": {"algorithmic_bytes": total_bytes,
+                                        "achieved": total_bytes / (ms_step * 1e-3) / 1e9,
+                                        "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                         "stage_ms_per_launch": per_launch},
+            "e2e": {"value": e2e_val, "unit": "events/s",
+                    "h2d_bytes_per_step": int(ev_p.numel() * 4 + cg_p.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            dt, n_ev = cpu_reference_step(cfg, w, cg_h, ev_h, npos)
+            cores = os.cpu_count() or 1
+            line["cpu_baseline"] = {
+                "value": n_ev / dt, "unit": "events/s", "cores": cores, "kind": "port",
+                "sample": f"1 window ({n_ev} events) fwd+bwd in {dt:.2f} s: numpy event stage "
+                          f"(1 thread) + C/OpenMP exhaustive KNN ({cores} threads)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="dsec", choices=["dsec", "dsec_tref5", "evimo2", "k3_det"])
+    ap.add_argument("--events", type=int, default=None, help="events per window (default: lognormal ~1e6)")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
+    ap.add_argument("--prof-warmup", type=int, default=None, help="override the >=3 warm-up rule (ncu runs only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,18 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
 int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, int32_t mode,
                            void *stream);
 
+/* Measurement hooks (bench.py / profiles): per-stage device time from cudaEvent pairs recorded on
+ * the launching stream around every kernel of cmax_forward / cmax_backward / the front end.
+ * enable(1) starts recording (up to 8192 stage launches), read() synchronises on the recorded
+ * events, returns the summed milliseconds and launch counts per stage and clears the buffer.
+ * Not thread safe (one caller thread per process, as in the reference). */
+int cmax_stage_count(void);
+const char *cmax_stage_name(int stage);
+int cmax_stage_timing_enable(int on);
+int cmax_stage_timing_read(double *ms_sum /* [cmax_stage_count()] */, int64_t *count);
+/* Number of kernels this library has launched since it was loaded. */
+int64_t cmax_launch_count(void);
+
 /* Reads the status words the kernels keep in the workspace (host call, synchronises `stream`):
  * out[0] = events skipped because their LUT cell index was out of range, out[1..3] reserved. */
 int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream);

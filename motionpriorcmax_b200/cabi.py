@@ -20,7 +20,8 @@ EXPORTS = (
     "cmax_abi_version", "cmax_error_string", "cmax_workspace_bytes", "cmax_forward",
     "cmax_backward", "cmax_create_iwe", "cmax_count_image", "cmax_knn_workspace_bytes",
     "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
-    "cmax_atomic_microbench", "cmax_read_status",
+    "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
+    "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
 )
 
 
@@ -80,6 +81,14 @@ def load():
     lib.cmax_atomic_microbench.argtypes = [P, c_int64, c_int64, c_int32, P]
     lib.cmax_read_status.restype = c_int32
     lib.cmax_read_status.argtypes = [P, POINTER(c_int64 * 4), P]
+    lib.cmax_stage_count.restype = c_int32
+    lib.cmax_stage_name.restype = c_char_p
+    lib.cmax_stage_name.argtypes = [c_int32]
+    lib.cmax_stage_timing_enable.restype = c_int32
+    lib.cmax_stage_timing_enable.argtypes = [c_int32]
+    lib.cmax_stage_timing_read.restype = c_int32
+    lib.cmax_stage_timing_read.argtypes = [P, P]
+    lib.cmax_launch_count.restype = c_int64
     if lib.cmax_abi_version() != 1:
         raise RuntimeError("libcmax_b200.so ABI version mismatch")
     _lib = lib
@@ -115,6 +124,17 @@ def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_sup
     c.smooth_weight = float(smooth_weight)
     c.deterministic = int(bool(deterministic))
     return c
+
+
+def stage_timing_read():
+    """{stage name: (total ms, launches)} since stage timing was enabled / last read."""
+    lib = load()
+    n = lib.cmax_stage_count()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(lib.cmax_stage_timing_read(ctypes.cast(ms, c_void_p), ctypes.cast(cnt, c_void_p)),
+          "cmax_stage_timing_read")
+    return {lib.cmax_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
 
 
 def ptr(t) -> c_void_p:

@@ -13,6 +13,44 @@ int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, floa
                 cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
+// stage timing / launch counting (single-threaded caller per process, like the reference)
+// ---------------------------------------------------------------------------------------------
+static const char *kStageNames[ST_COUNT] = {
+    "bin_points", "knn_select", "event_forward", "image_forward", "smooth_forward", "finalize",
+    "image_backward", "smooth_backward", "event_backward", "lut_backward", "traj_forward",
+    "traj_backward"};
+constexpr int kMaxTimed = 8192;
+static bool g_timing = false;
+static cudaEvent_t g_ev[kMaxTimed][2];
+static int g_ev_stage[kMaxTimed];
+static int g_ev_created = 0, g_ev_used = 0;
+static int g_open[ST_COUNT];
+static long long g_launches = 0;
+
+void count_launch(int n) { g_launches += n; }
+
+void stage_begin(int stage, cudaStream_t st)
+{
+    g_open[stage] = -1;
+    if (!g_timing || g_ev_used >= kMaxTimed) return;
+    if (g_ev_used >= g_ev_created) {
+        if (cudaEventCreate(&g_ev[g_ev_created][0]) != cudaSuccess) return;
+        if (cudaEventCreate(&g_ev[g_ev_created][1]) != cudaSuccess) return;
+        ++g_ev_created;
+    }
+    const int i = g_ev_used++;
+    g_ev_stage[i] = stage;
+    g_open[stage] = i;
+    cudaEventRecord(g_ev[i][0], st);
+}
+
+void stage_end(int stage, cudaStream_t st)
+{
+    if (g_open[stage] >= 0) cudaEventRecord(g_ev[g_open[stage]][1], st);
+    g_open[stage] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
 void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g)
@@ -428,6 +466,8 @@ int cmax_trajectories_forward(const float *coeff_grid, const float *phi, int64_t
     const int o = patch / 2;
     const int ny = (H - o + patch - 1) / patch, nx = (W - o + patch - 1) / patch;
     dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
+    StageScope sc(ST_TRAJ_FWD, static_cast<cudaStream_t>(stream));
+    count_launch();
     traj_forward_kernel<<<grid, 128, sizeof(float) * n_t * K, static_cast<cudaStream_t>(stream)>>>(
         coeff_grid, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, add_offsets, trajectories_out);
     return check_launch();
@@ -445,6 +485,8 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
     const int ny = (H - o + patch - 1) / patch, nx = (W - o + patch - 1) / patch;
     cudaMemsetAsync(dcoeff_grid_out, 0, sizeof(float) * B * S * 2 * K * (int64_t)H * W, st);
     dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
+    StageScope sc(ST_TRAJ_BWD, st);
+    count_launch();
     traj_backward_kernel<<<grid, 128, sizeof(float) * n_t * K, st>>>(
         dtraj, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, dcoeff_grid_out);
     return check_launch();
@@ -457,6 +499,7 @@ int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, 
         return CMAX_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = 148 * 8;
+    count_launch();
     if (mode == 0)
         atomic_bench_kernel<0><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
     else if (mode == 1)
@@ -467,6 +510,37 @@ int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, 
         return CMAX_ERR_BAD_CONFIG;
     return check_launch();
 }
+
+int cmax_stage_count(void) { return ST_COUNT; }
+
+const char *cmax_stage_name(int stage)
+{
+    return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : "";
+}
+
+int cmax_stage_timing_enable(int on)
+{
+    g_timing = on != 0;
+    g_ev_used = 0;
+    return CMAX_OK;
+}
+
+int cmax_stage_timing_read(double *ms_sum, int64_t *count)
+{
+    if (!ms_sum || !count) return CMAX_ERR_BAD_SHAPE;
+    for (int i = 0; i < ST_COUNT; ++i) { ms_sum[i] = 0.0; count[i] = 0; }
+    for (int i = 0; i < g_ev_used; ++i) {
+        if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) return CMAX_ERR_CUDA;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) != cudaSuccess) return CMAX_ERR_CUDA;
+        ms_sum[g_ev_stage[i]] += ms;
+        count[g_ev_stage[i]] += 1;
+    }
+    g_ev_used = 0;
+    return CMAX_OK;
+}
+
+int64_t cmax_launch_count(void) { return g_launches; }
 
 int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream)
 {

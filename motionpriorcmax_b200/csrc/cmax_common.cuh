@@ -80,6 +80,21 @@ int launch_finalize_losses(const Geom &g, const Layout &L, char *ws, float *loss
 
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? CMAX_OK : CMAX_ERR_CUDA; }
 
+// ---- optional per-stage timing (cudaEvent pairs on the launching stream) and launch counter ----
+enum Stage {
+    ST_BIN_POINTS = 0, ST_KNN_SELECT, ST_EVENT_FWD, ST_IMAGE_FWD, ST_SMOOTH_FWD, ST_FINALIZE,
+    ST_IMAGE_BWD, ST_SMOOTH_BWD, ST_EVENT_BWD, ST_LUT_BWD, ST_TRAJ_FWD, ST_TRAJ_BWD, ST_COUNT
+};
+void stage_begin(int stage, cudaStream_t st);
+void stage_end(int stage, cudaStream_t st);
+void count_launch(int n = 1);
+struct StageScope {
+    int id;
+    cudaStream_t st;
+    StageScope(int i, cudaStream_t s) : id(i), st(s) { stage_begin(id, st); }
+    ~StageScope() { stage_end(id, st); }
+};
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // device helpers

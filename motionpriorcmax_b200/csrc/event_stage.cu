@@ -209,6 +209,7 @@ int launch_splat(int mode, const float *events, const float *weight, int64_t nb,
 {
     if (M == 0 || nb == 0) return CMAX_OK;
     dim3 grid((unsigned)((M + 255) / 256), (unsigned)nb);
+    count_launch();
     if (mode == 0)
         splat_kernel<0><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
     else if (mode == 1)
@@ -236,6 +237,8 @@ int launch_event_forward(const Geom &g, const Layout &L, const float *events, co
     long long *raw_i64 = reinterpret_cast<long long *>(ws + L.raw_i64);
     long long *status = reinterpret_cast<Header *>(ws + L.header)->status;
     const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    StageScope sc(ST_EVENT_FWD, st);
+    count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
     if (g.det)
         cudaMemsetAsync(raw_i64, 0, sizeof(long long) * count, st);
     else
@@ -260,6 +263,8 @@ int launch_event_backward(const Geom &g, const Layout &L, const float *events, c
     const float *dimg = reinterpret_cast<const float *>(ws + L.dimg);
     float *dlut = reinterpret_cast<float *>(ws + L.dlut);
     long long *dlut_i64 = reinterpret_cast<long long *>(ws + L.dlut_i64);
+    StageScope sc(ST_EVENT_BWD, st);
+    count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
     if (g.det) cudaMemsetAsync(dlut_i64, 0, sizeof(long long) * count, st);
     if (g.M > 0) {
         dim3 grid((unsigned)((g.M + 255) / 256), (unsigned)g.B);

@@ -372,6 +372,7 @@ int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, floa
                 cudaStream_t st)
 {
     dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)planes);
+    count_launch();
     blur_kernel<<<grid, dim3(32, 8), 0, st>>>(raw, out, H, W, gauss3(sigma));
     return check_launch();
 }
@@ -380,6 +381,8 @@ int launch_image_forward(const Geom &g, const Layout &L, char *ws, float *iwes_o
 {
     const int64_t planes = g.B * g.R * g.P;
     dim3 grid((g.W + T - 1) / T, (g.H + T - 1) / T, (unsigned)planes);
+    StageScope sc(ST_IMAGE_FWD, st);
+    count_launch();
     image_forward_kernel<<<grid, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const float *>(ws + L.raw), iwes_out, g.H, g.W, gauss3(1.0f), g.l2focus,
         reinterpret_cast<double *>(ws + L.focus_partials));
@@ -390,6 +393,8 @@ int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t
 {
     const int64_t planes = g.B * g.R * g.P;
     dim3 grid((g.W + T - 1) / T, (g.H + T - 1) / T, (unsigned)planes);
+    StageScope sc(ST_IMAGE_BWD, st);
+    count_launch();
     image_backward_kernel<<<grid, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const float *>(ws + L.raw), reinterpret_cast<float *>(ws + L.dimg), g.H,
         g.W, gauss3(1.0f), g.l2focus);
@@ -422,6 +427,8 @@ int launch_smooth_forward(const Geom &g, const Layout &L, char *ws, cudaStream_t
     smooth_field(g, L, ws, &field, &F, &Rv, &go);
     if (F == 0) return CMAX_OK;
     dim3 grid((g.Wq + ST_W - 1) / ST_W, (g.Hq + ST_H - 1) / ST_H, (unsigned)(F * Rv));
+    StageScope sc(ST_SMOOTH_FWD, st);
+    count_launch();
     smooth_forward_kernel<<<grid, dim3(ST_W, ST_H), 0, st>>>(
         field, g.Hq, g.Wq, Rv, reinterpret_cast<double *>(ws + L.smooth_partials));
     return check_launch();
@@ -432,6 +439,7 @@ int launch_smooth_backward(const Geom &g, const Layout &L, const float *grad_los
 {
     // dLUT must start from the smoothness gradient (on_flow_to_tref) or from zero
     const bool on = g.smooth_w != 0.0f;
+    StageScope sc(ST_SMOOTH_BWD, st);
     const size_t dlut_bytes = sizeof(float) * g.S * g.q * g.R * 2;
     if (!on || g.smooth_next) cudaMemsetAsync(ws + L.dlut, 0, dlut_bytes, st);
     if (!on) return check_launch();
@@ -443,6 +451,7 @@ int launch_smooth_backward(const Geom &g, const Layout &L, const float *grad_los
     if (F == 0) return check_launch();
     const double cnt = (double)F * Rv * 2.0 * g.Hq * g.Wq;       // elements of dx (== of dy)
     dim3 grid((g.Wq + ST_W - 1) / ST_W, (g.Hq + ST_H - 1) / ST_H, (unsigned)(F * Rv));
+    count_launch();
     smooth_backward_kernel<<<grid, dim3(ST_W, ST_H), 0, st>>>(
         field, g.Hq, g.Wq, Rv, grad_loss, (float)((double)g.smooth_w / (2.0 * cnt)),
         reinterpret_cast<float *>(ws + go));
@@ -461,6 +470,8 @@ int launch_finalize_losses(const Geom &g, const Layout &L, char *ws, float *loss
         ns = (int)(F * Rv) * ((g.Wq + ST_W - 1) / ST_W) * ((g.Hq + ST_H - 1) / ST_H);
         n_smooth = (double)F * Rv * 2.0 * g.Hq * g.Wq;
     }
+    StageScope sc(ST_FINALIZE, st);
+    count_launch();
     finalize_losses_kernel<<<1, 256, 0, st>>>(
         reinterpret_cast<Header *>(ws + L.header),
         reinterpret_cast<const double *>(ws + L.focus_partials), L.n_img_blocks,

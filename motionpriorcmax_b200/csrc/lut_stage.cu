@@ -414,10 +414,16 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
                              kMaxKnn * kKnnBlock * 8);
         attr_done = true;
     }
-    bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, cell_start, sorted);
+    {
+        StageScope sc(ST_BIN_POINTS, st);
+        bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, cell_start, sorted);
+        count_launch();
+    }
     const int tiles = ((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
     dim3 grid(tiles, (unsigned)g.S);
     size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
+    StageScope sc(ST_KNN_SELECT, st);
+    count_launch();
     if (ind_out != nullptr) {
         knn_select_kernel<1><<<grid, kKnnBlock, smem_heap, st>>>(
             traj, g, cell_start, sorted, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -444,6 +450,8 @@ int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char 
     const int *jcut = reinterpret_cast<const int *>(ws + L.jcut);
     const float *wsum = reinterpret_cast<const float *>(ws + L.wsum);
     const unsigned *tmax = reinterpret_cast<const unsigned *>(ws + L.tau_max);
+    StageScope sc(ST_LUT_BWD, st);
+    count_launch();
     const float *dlut = reinterpret_cast<const float *>(ws + L.dlut);
     const float *df2n = want_next ? reinterpret_cast<const float *>(ws + L.df2n) : nullptr;
     if (g.R == 1)

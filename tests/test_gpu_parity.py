@@ -36,6 +36,22 @@ def _run_loss(cfg, traj, times, events, npos, deterministic=False, grad_scale=1.
                 dtraj=t.grad.cpu().numpy(), loss_t=loss)
 
 
+def _assert_grad_close(got, truth64, cfg, traj, times, ev, npos, tol=2 * TOL):
+    """Norm-wise 1e-5-class check of d loss / d trajectories.  With the l1 focus norm the
+    gradient contains sign(Sobel response); a pixel whose response is ~0 flips its sign between
+    float32 and float64 evaluation (SURVEY.md section 7 "hard parts"), which moves the gradient
+    by far more than rounding.  The CUDA path follows the reference's float32 arithmetic, so in
+    that case it must agree with the float32 oracle (which mirrors the reference op for op)."""
+    from oracle import focus_oracle as fo
+    e64 = rel_err(got, truth64)
+    if e64 < tol:
+        return
+    o32 = fo.FocusOracle(**cfg, dtype=np.float32)
+    o32.forward(traj, times, ev, npos)
+    e32 = rel_err(got, o32.backward()["dtraj"])
+    assert cfg["focus_loss_norm"] == "l1" and e32 < tol, (e64, e32)
+
+
 # ------------------------------------------------------------------------------------------
 # golden vectors of the real reference
 # ------------------------------------------------------------------------------------------
@@ -200,7 +216,7 @@ def test_loss_matches_oracle_midsize(variant):
     assert abs(r["smooth"] - f["smoothness_loss"]) <= TOL * max(abs(f["smoothness_loss"]), 1e-3)
     assert rel_err(r["iwes"], f["iwes"]) < TOL
     assert rel_err(r["lut"], f["flow_lut"]) < TOL
-    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL     # l1 sign() flips on ~0 Sobel responses
+    _assert_grad_close(r["dtraj"], g["dtraj"], base, traj, times, ev, npos)
 
 
 def test_deterministic_mode_is_bit_reproducible_and_close():
@@ -256,7 +272,7 @@ def test_full_size_dsec_window_matches_oracle():
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(r["iwes"], f["iwes"]) < TOL
     assert rel_err(r["lut"], f["flow_lut"]) < TOL
-    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos)
 
 
 def test_properties_at_full_size():
