@@ -151,6 +151,9 @@ int cmax_stage_timing_enable(int on);
 int cmax_stage_timing_read(double *ms_sum /* [cmax_stage_count()] */, int64_t *count);
 /* Number of kernels this library has launched since it was loaded. */
 int64_t cmax_launch_count(void);
+/* Inspection: how many LUT queries of the most recent cmax_forward / cmax_knn_indices call left
+ * the staged fast path for the heap search (host call, synchronises `stream`; -1 if unknown). */
+int64_t cmax_last_worklist_count(void *stream);
 
 /* Reads the status words the kernels keep in the workspace (host call, synchronises `stream`):
  * out[0] = events skipped because their LUT cell index was out of range, out[1..3] reserved. */

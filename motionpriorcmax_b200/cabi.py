@@ -22,6 +22,7 @@ EXPORTS = (
     "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
     "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
+    "cmax_last_worklist_count",
 )
 
 
@@ -89,6 +90,8 @@ def load():
     lib.cmax_stage_timing_read.restype = c_int32
     lib.cmax_stage_timing_read.argtypes = [P, P]
     lib.cmax_launch_count.restype = c_int64
+    lib.cmax_last_worklist_count.restype = c_int64
+    lib.cmax_last_worklist_count.argtypes = [P]
     if lib.cmax_abi_version() != 1:
         raise RuntimeError("libcmax_b200.so ABI version mismatch")
     _lib = lib

@@ -11,6 +11,7 @@ int launch_splat(int mode, const float *events, const float *weight, int64_t nb,
 int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStream_t st);
 int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
                 cudaStream_t st);
+extern const int *g_last_work_count;
 
 // ---------------------------------------------------------------------------------------------
 // stage timing / launch counting (single-threaded caller per process, like the reference)
@@ -84,6 +85,7 @@ void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g)
     double rk = sqrt((double)K / (3.14159265358979 * (dens > 0 ? dens : 1e-9)));
     int r0 = (int)ceil((rk - 0.5 * g->cs) / g->cs);
     g->r0 = r0 < 0 ? 0 : (r0 > 8 ? 8 : r0);
+    g->r_fast = g->r0 + 1;
 }
 
 int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos, Geom *g)
@@ -126,6 +128,37 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     return CMAX_OK;
 }
 
+template <class Take>
+static void take_knn(const Geom &g, Layout &L, Take &take)
+{
+    const size_t tiles = (size_t)((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
+    L.cell_start = take(sizeof(int) * g.S * (g.NC + 1));
+    L.sorted = take(sizeof(float4) * g.S * g.n);
+    L.sflow = take(g.R == 1 ? sizeof(float2) * g.S * g.n : 16);
+    L.tau = take(sizeof(float) * g.S * g.q);
+    L.jcut = take(sizeof(int) * g.S * g.q);
+    L.wsum = take(g.iwd ? sizeof(float) * g.S * g.q : 16);
+    L.tau_max = take(sizeof(unsigned) * g.S);
+    L.tile_max = take(sizeof(unsigned) * g.S * tiles);
+    L.worklist = take(sizeof(int) * g.S * g.q);
+    L.work_count = take(sizeof(int));
+}
+
+Layout make_knn_layout(const Geom &g)
+{
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    take_knn(g, L, take);
+    L.total = off;
+    return L;
+}
+
 Layout make_layout(const Geom &g)
 {
     Layout L;
@@ -146,12 +179,7 @@ Layout make_layout(const Geom &g)
     L.header = take(1024);
     L.focus_partials = take(sizeof(double) * L.n_img_blocks);
     L.smooth_partials = take(sizeof(double) * (L.n_sm_blocks > 0 ? L.n_sm_blocks : 1));
-    L.cell_start = take(sizeof(int) * g.S * (g.NC + 1));
-    L.sorted = take(sizeof(float4) * g.S * g.n);
-    L.tau = take(sizeof(float) * g.S * g.q);
-    L.jcut = take(sizeof(int) * g.S * g.q);
-    L.wsum = take(g.iwd ? sizeof(float) * g.S * g.q : 16);
-    L.tau_max = take(sizeof(unsigned) * g.S);
+    take_knn(g, L, take);
     L.lut = take(sizeof(float) * nlut);
     L.f2n = take(sizeof(float) * (nf2n > 0 ? nf2n : 4));
     L.raw = take(sizeof(float) * npix);
@@ -424,7 +452,7 @@ size_t cmax_knn_workspace_bytes(int32_t H, int32_t W, int32_t s, int64_t S, int6
 {
     Geom g;
     if (knn_only_geom(H, W, s, S, n, K, &g) != CMAX_OK) return 0;
-    return align_up(sizeof(int) * S * (g.NC + 1)) + align_up(sizeof(float4) * S * n);
+    return make_knn_layout(g).total;
 }
 
 int cmax_knn_indices(const float *points, int64_t S, int64_t n, int32_t H, int32_t W, int32_t s,
@@ -436,12 +464,8 @@ int cmax_knn_indices(const float *points, int64_t S, int64_t n, int32_t H, int32
     if (rc != CMAX_OK) return rc;
     if (!points || !ind_out) return CMAX_ERR_BAD_SHAPE;
     g.l1dist = dist_norm == CMAX_NORM_L1;
-    Layout L;
-    memset(&L, 0, sizeof(L));
-    L.cell_start = 0;
-    L.sorted = align_up(sizeof(int) * S * (g.NC + 1));
-    if (!workspace || ((uintptr_t)workspace & 255u) ||
-        workspace_bytes < L.sorted + align_up(sizeof(float4) * S * n))
+    const Layout L = make_knn_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
         return CMAX_ERR_WORKSPACE;
     return launch_lut_forward(g, L, points, static_cast<char *>(workspace), nullptr, ind_out,
                               dist_out, static_cast<cudaStream_t>(stream));
@@ -541,6 +565,16 @@ int cmax_stage_timing_read(double *ms_sum, int64_t *count)
 }
 
 int64_t cmax_launch_count(void) { return g_launches; }
+
+int64_t cmax_last_worklist_count(void *stream)
+{
+    if (!g_last_work_count) return -1;
+    int v = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(&v, g_last_work_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    return v;
+}
 
 int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream)
 {

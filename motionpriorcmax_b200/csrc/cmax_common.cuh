@@ -33,7 +33,8 @@ struct Geom {                 // derived sizes, passed by value to kernels
     float off;                // s/2 - 0.5 (focus.py:117)
     int Hc, Wc, NC;           // cell list
     float cs, inv_cs;         // cell edge (multiple of s)
-    int r0;                   // initial search radius in cells
+    int r0;                   // initial search radius in cells (heap path)
+    int r_fast;               // window radius of the staged fast path
     int l1dist, l2focus, scale_dt, mask_border, pab, iwd, smooth_next, det;
     float smooth_w;
     int64_t B, M, n, S;       // S = B * nb
@@ -50,8 +51,8 @@ struct Header {               // first 1 KiB of the workspace
 };
 
 struct Layout {
-    size_t header, focus_partials, smooth_partials, cell_start, sorted, tau, jcut, wsum, tau_max,
-        lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
+    size_t header, focus_partials, smooth_partials, cell_start, sorted, sflow, tau, jcut, wsum,
+        tau_max, tile_max, worklist, work_count, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
     int n_img_blocks, n_sm_blocks;
 };
 
@@ -60,6 +61,7 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 int make_geom(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, int64_t npos, Geom *g);
 void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g);
 Layout make_layout(const Geom &g);
+Layout make_knn_layout(const Geom &g);     // only the fields the KNN kernels touch
 
 // ---- launchers (each returns cudaGetLastError() != cudaSuccess ? CMAX_ERR_CUDA : CMAX_OK) ----
 int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,

@@ -3,19 +3,29 @@
 // The reference finds, for every LUT cell centre (q = Hq*Wq queries) and every (sample, bin)
 // slab, the K nearest of the n trajectory positions at t_mid[bin] by exhaustive KeOps search
 // (n*q distance evaluations per slab), gathers their displacement to each reference time and
-// averages.  Here:
-//   1. bin_points_kernel     one CTA per slab: counting sort of the n points into a uniform
-//                            cell list held in shared memory, runs ordered by trajectory index
-//                            (so every later traversal order is deterministic);
-//   2. knn_select_kernel     one thread per query: exact K-NN by ring search over the cell
-//                            list with a shared-memory max-heap keyed on (distance, index);
-//                            emits the LUT (and flow_to_next), and instead of the K indices
-//                            only the K-th key (tau, jcut) - 8 B per query instead of 2*K B;
-//   3. lut_backward_kernel   one thread per trajectory: *gathers* d loss/d LUT from every query
-//                            whose K-set contains it (membership = key <= (tau, jcut),
-//                            re-evaluated with bit-identical distance arithmetic): no atomics,
-//                            deterministic, and no K-index tensor ever touches HBM.
-// Exactness: identical to exhaustive search with "lowest index wins" ties (see oracle).
+// averages.  Here (all exact, ties broken by lowest trajectory index - see oracle):
+//   1. bin_points_kernel   one CTA per slab: counting sort of the n points into a uniform cell
+//                          list held in shared memory, runs ordered by trajectory index (every
+//                          later traversal order is therefore deterministic); also emits the
+//                          flow-to-t_ref of every point in sorted order when R == 1.
+//   2. knn_fast_kernel     one CTA per 16x8 tile of queries, one thread per query.  The points
+//                          of the tile's cell window are staged once in shared memory (SoA).
+//                          Each thread finds its exact K-th neighbour key (tau, jcut) in
+//                          (distance, index) order with two streaming passes over its own
+//                          (2r+1)^2 cells: pass 1 = packed 8-bucket histogram of the squared
+//                          distance around a density-based estimate, pass 2 = members below the
+//                          boundary bucket are accumulated on the fly, the handful of candidates
+//                          inside it are ordered exactly.  Queries the window cannot settle go
+//                          to a work list.
+//   3. knn_heap_kernel     work-list queries: ring search over the global cell list with a
+//                          shared-memory max-heap (any density, any K <= 192).
+//   4. lut_accumulate_kernel   generic accumulation of LUT / flow_to_next / iwd weights from
+//                          (tau, jcut) for everything step 2 did not fuse.
+//   5. lut_backward_kernel one thread per trajectory: *gathers* d loss/d LUT from every query
+//                          whose K-set contains it (membership = key <= (tau, jcut), re-evaluated
+//                          with bit-identical distance arithmetic); the search window is bounded
+//                          per 16x8-query tile by that tile's largest tau.  No atomics, no K-index
+//                          tensor in HBM: 8 B per query (tau, jcut) is all the backward needs.
 #include "cmax_common.cuh"
 
 namespace cmax {
@@ -38,8 +48,9 @@ __device__ __forceinline__ const float2 *slab_points(const float *traj, const Ge
 
 __global__ void __launch_bounds__(1024)
 bin_points_kernel(const float *__restrict__ traj, Geom g, int *__restrict__ cell_start,
-                  float4 *__restrict__ sorted)
+                  float4 *__restrict__ sorted, float2 *__restrict__ sflow)
 {
+    // record = (y, x, trajectory index, unused); sflow = traj(t_ref) - traj(t_mid) when R == 1
     extern __shared__ int cnt[];                 // [NC] counters, then cursors
     __shared__ int warp_tot[32];
     const int64_t slab = blockIdx.x;
@@ -114,10 +125,21 @@ bin_points_kernel(const float *__restrict__ traj, Geom g, int *__restrict__ cell
             }
         }
     }
+    if (sflow != nullptr) {                       // R == 1: flow to the reference time, sorted order
+        __syncthreads();
+        const int64_t b = slab / g.nb;
+        const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb)) * g.n;
+        float2 *fo = sflow + slab * g.n;
+        for (int64_t i = tid; i < g.n; i += nt) {
+            const float4 r = out[i];
+            const float2 pr = __ldg(tref + __float_as_int(r.z));
+            fo[i] = make_float2(__fsub_rn(pr.x, r.x), __fsub_rn(pr.y, r.y));     // focus.py:141
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2. exact K-NN selection + LUT interpolation
+// shared helpers: per-thread heap, cell-window traversal over the *global* cell list
 // ---------------------------------------------------------------------------------------------
 struct Heap {                       // per-thread max-heap on (d, j), column `tid` of two smem arrays
     float *hd;
@@ -171,162 +193,456 @@ struct Heap {                       // per-thread max-heap on (d, j), column `ti
     }
 };
 
-__device__ __forceinline__ void scan_cells(Heap &h, const int *__restrict__ cstart,
+// Visit every point of the cells [row, c0..c1] (clipped): f(distance, record)
+template <class F>
+__device__ __forceinline__ void scan_cells(const int *__restrict__ cstart,
                                            const float4 *__restrict__ sorted, int row, int c0,
-                                           int c1, const Geom &g, float qy, float qx)
+                                           int c1, const Geom &g, float qy, float qx, F &&f)
 {
     if (row < 0 || row >= g.Hc) return;
     c0 = max(c0, 0);
     c1 = min(c1, g.Wc - 1);
     if (c0 > c1) return;
-    int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
+    const int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
     for (int i = a; i < e; ++i) {
-        float4 r = __ldg(sorted + i);
-        h.consider(knn_dist(qy, qx, r.x, r.y, g.l1dist), __float_as_int(r.z));
+        const float4 r = __ldg(sorted + i);
+        f(knn_dist(qy, qx, r.x, r.y, g.l1dist), r);
     }
 }
 
-// EMIT: 0 = LUT (+tau/jcut/wsum/f2n) for the loss, 1 = sorted neighbour lists (test entry)
-template <int EMIT>
-__global__ void __launch_bounds__(kKnnBlock)
-knn_select_kernel(const float *__restrict__ traj, Geom g, const int *__restrict__ cell_start,
-                  const float4 *__restrict__ sorted_all, float *__restrict__ lut,
-                  float *__restrict__ f2n, float *__restrict__ tau, int *__restrict__ jcut,
-                  float *__restrict__ wsum, unsigned *__restrict__ tau_max,
-                  float *__restrict__ lut_copy, int32_t *__restrict__ ind_out,
-                  float *__restrict__ dist_out)
+template <class F>
+__device__ __forceinline__ void scan_window(const int *__restrict__ cstart,
+                                            const float4 *__restrict__ sorted, int cqy, int cqx,
+                                            int r, const Geom &g, float qy, float qx, F &&f)
 {
-    extern __shared__ float heap_mem[];
+    for (int row = cqy - r; row <= cqy + r; ++row)
+        scan_cells(cstart, sorted, row, cqx - r, cqx + r, g, qy, qx, f);
+}
+
+// lower bound on the (squared, for l2) distance of every point outside the (2r+1)^2 cell window
+// around (cqy, cqx); +inf when the window covers the whole grid
+__device__ __forceinline__ float window_bound(int cqy, int cqx, int r, const Geom &g, float qy, float qx)
+{
+    float bnd = INFINITY;
+    if (cqy - r > 0) bnd = fminf(bnd, qy - (float)(cqy - r) * g.cs);
+    if (cqy + r < g.Hc - 1) bnd = fminf(bnd, (float)(cqy + r + 1) * g.cs - qy);
+    if (cqx - r > 0) bnd = fminf(bnd, qx - (float)(cqx - r) * g.cs);
+    if (cqx + r < g.Wc - 1) bnd = fminf(bnd, (float)(cqx + r + 1) * g.cs - qx);
+    if (bnd == INFINITY) return bnd;
+    bnd = bnd * (1.0f - 1e-5f);              // cells are assigned with a rounded product
+    return g.l1dist ? bnd : bnd * bnd;
+}
+
+// smallest window radius whose bound exceeds t (so every point with d <= t is inside)
+__device__ __forceinline__ int radius_for(float t, int cqy, int cqx, const Geom &g, float qy, float qx)
+{
+    int r = 0;
+    while (true) {
+        const float bnd = window_bound(cqy, cqx, r, g, qy, qx);
+        if (bnd == INFINITY || t < bnd) return r;
+        ++r;
+    }
+}
+
+struct Query {
+    int iy, ix, cqy, cqx;
+    float qy, qx;
+};
+
+__device__ __forceinline__ Query make_query(int c, const Geom &g)
+{
+    Query q;
+    q.iy = c / g.Wq;
+    q.ix = c - q.iy * g.Wq;
+    q.qy = __fadd_rn((float)(q.iy * g.s), g.off);      // focus.py:118-123
+    q.qx = __fadd_rn((float)(q.ix * g.s), g.off);
+    q.cqy = min((int)floorf(q.qy * g.inv_cs), g.Hc - 1);
+    q.cqx = min((int)floorf(q.qx * g.inv_cs), g.Wc - 1);
+    return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. fast path
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageCap = 1280;    // points staged per CTA
+constexpr int kListCap = 12;       // boundary-bucket candidates kept per thread
+constexpr int kWinRows = kKnnTileH + 2 * 10;
+constexpr int kWinCols = kKnnTileW + 2 * 10;
+
+// bucket 0: d < lo; buckets 1..7: seven slices of [lo, hi); 8: d >= hi (not counted)
+__device__ __forceinline__ int bucket_of(float d, float lo, float invw)
+{
+    const float v = __fmul_rn(__fsub_rn(d, lo), invw);
+    return d < lo ? 0 : min(__float2int_rd(v) + 1, 8);
+}
+
+template <bool L1D, bool FUSED>
+__global__ void __launch_bounds__(kKnnBlock)
+knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
+                const float2 *__restrict__ sflow_all, float *__restrict__ lut,
+                float *__restrict__ lut_copy, float *__restrict__ tau, int *__restrict__ jcut,
+                unsigned *__restrict__ tau_max, unsigned *__restrict__ tile_max,
+                int *__restrict__ worklist, int *__restrict__ work_count)
+{
+    __shared__ float s_py[kStageCap], s_px[kStageCap];
+    __shared__ int s_pj[kStageCap];
+    __shared__ float2 s_fl[FUSED ? kStageCap : 1];
+    __shared__ int s_cell[kWinRows][kWinCols + 1];
+    __shared__ float s_ld[kListCap][kKnnBlock];
+    __shared__ int s_li[kListCap][kKnnBlock];
+    __shared__ int s_rowbase[kWinRows + 1];
     __shared__ unsigned blk_max;
+
     const int tid = threadIdx.x;
-    const int64_t slab = blockIdx.y;
+    const int slab = blockIdx.y;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
     const bool active = iy < g.Hq && ix < g.Wq;
+    const int r = g.r_fast;
+    const int *cstart = cell_start + (int64_t)slab * (g.NC + 1);
+    const float4 *sorted = sorted_all + (int64_t)slab * g.n;
+
+    // ---- the tile's cell window -----------------------------------------------------------
+    const int ly0 = ty * kKnnTileH, ly1 = min(ly0 + kKnnTileH - 1, g.Hq - 1);
+    const int lx0 = tx * kKnnTileW, lx1 = min(lx0 + kKnnTileW - 1, g.Wq - 1);
+    const int wy0 = max(min((int)floorf(((float)(ly0 * g.s) + g.off) * g.inv_cs), g.Hc - 1) - r, 0);
+    const int wy1 = min(min((int)floorf(((float)(ly1 * g.s) + g.off) * g.inv_cs), g.Hc - 1) + r, g.Hc - 1);
+    const int wx0 = max(min((int)floorf(((float)(lx0 * g.s) + g.off) * g.inv_cs), g.Wc - 1) - r, 0);
+    const int wx1 = min(min((int)floorf(((float)(lx1 * g.s) + g.off) * g.inv_cs), g.Wc - 1) + r, g.Wc - 1);
+    const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 1;
+
     if (tid == 0) blk_max = 0u;
+    if (tid < 32) {                                   // row run lengths -> exclusive scan
+        int len = 0;
+        if (tid < nrow)
+            len = __ldg(cstart + (wy0 + tid) * g.Wc + wx1 + 1) - __ldg(cstart + (wy0 + tid) * g.Wc + wx0);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        if (tid < nrow) s_rowbase[tid] = incl - len;
+        if (tid == nrow - 1) s_rowbase[nrow] = incl;
+    }
+    __syncthreads();
+    const int total = s_rowbase[nrow];
+    const bool staged = total <= kStageCap;           // CTA-uniform
+    if (staged) {
+        for (int i = tid; i < nrow * (ncol + 1); i += kKnnBlock) {
+            const int lr = i / (ncol + 1), lc = i - lr * (ncol + 1);
+            const int ga = __ldg(cstart + (wy0 + lr) * g.Wc + wx0);
+            s_cell[lr][lc] = __ldg(cstart + (wy0 + lr) * g.Wc + wx0 + lc) - ga + s_rowbase[lr];
+        }
+        for (int lr = 0; lr < nrow; ++lr) {
+            const int ga = __ldg(cstart + (wy0 + lr) * g.Wc + wx0);
+            const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base;
+            for (int k = tid; k < len; k += kKnnBlock) {
+                const float4 rec = __ldg(sorted + ga + k);
+                s_py[base + k] = rec.x;
+                s_px[base + k] = rec.y;
+                s_pj[base + k] = __float_as_int(rec.z);
+                if (FUSED) s_fl[base + k] = __ldg(sflow_all + (int64_t)slab * g.n + ga + k);
+            }
+        }
+    }
     __syncthreads();
 
-    Heap h;
-    h.hd = heap_mem + tid;
-    h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * kKnnBlock) + tid;
-    h.K = g.K;
-    h.cnt = 0;
-    h.rootd = INFINITY;
-    h.rootj = 0x7fffffff;
-
-    if (active) {
-        const int *cstart = cell_start + slab * (g.NC + 1);
-        const float4 *sorted = sorted_all + slab * g.n;
-        const float qy = __fadd_rn((float)(iy * g.s), g.off);      // focus.py:118-123
+    bool resolved = false;
+    float t_d = 0.0f;
+    int t_j = 0;
+    float ay = 0.0f, ax = 0.0f;
+    if (active && staged) {
+        const float qy = __fadd_rn((float)(iy * g.s), g.off);
         const float qx = __fadd_rn((float)(ix * g.s), g.off);
         const int cqy = min((int)floorf(qy * g.inv_cs), g.Hc - 1);
         const int cqx = min((int)floorf(qx * g.inv_cs), g.Wc - 1);
-        int r = g.r0;
-        for (int row = cqy - r; row <= cqy + r; ++row)
-            scan_cells(h, cstart, sorted, row, cqx - r, cqx + r, g, qy, qx);
-        while (true) {
-            // lower bound on the distance of every point outside the (2r+1)^2 cell window
-            float bnd = INFINITY;
-            if (cqy - r > 0) bnd = fminf(bnd, qy - (float)(cqy - r) * g.cs);
-            if (cqy + r < g.Hc - 1) bnd = fminf(bnd, (float)(cqy + r + 1) * g.cs - qy);
-            if (cqx - r > 0) bnd = fminf(bnd, qx - (float)(cqx - r) * g.cs);
-            if (cqx + r < g.Wc - 1) bnd = fminf(bnd, (float)(cqx + r + 1) * g.cs - qx);
-            if (bnd == INFINITY) break;                    // window covers the whole grid
-            bnd = bnd * (1.0f - 1e-5f);
-            if (!g.l1dist) bnd = bnd * bnd;
-            if (h.cnt == h.K && h.rootd < bnd) break;      // strict: ties could still win on index
-            ++r;
-            scan_cells(h, cstart, sorted, cqy - r, cqx - r, cqx + r, g, qy, qx);
-            scan_cells(h, cstart, sorted, cqy + r, cqx - r, cqx + r, g, qy, qx);
-            for (int row = cqy - r + 1; row <= cqy + r - 1; ++row) {
-                scan_cells(h, cstart, sorted, row, cqx - r, cqx - r, g, qy, qx);
-                scan_cells(h, cstart, sorted, row, cqx + r, cqx + r, g, qy, qx);
+        const int r0w = max(cqy - r, 0) - wy0, r1w = min(cqy + r, g.Hc - 1) - wy0;
+        const int c0w = max(cqx - r, 0) - wx0, c1w = min(cqx + r, g.Wc - 1) - wx0 + 1;
+        const float bnd = window_bound(cqy, cqx, r, g, qy, qx);
+        int nwin = 0;
+        for (int lr = r0w; lr <= r1w; ++lr) nwin += s_cell[lr][c1w] - s_cell[lr][c0w];
+        // density-based estimate of the K-th key and the histogram bracket around it
+        const float area = (float)((r1w - r0w + 1) * (c1w - c0w)) * g.cs * g.cs;
+        float est = (float)g.K * area / (3.14159265f * (float)max(nwin, 1));
+        if (L1D) est = sqrtf(est * 1.5707963f);        // l1 ball of radius t has area 2 t^2
+        const float lo = 0.45f * est;
+        const float hi = fminf(1.7f * est, bnd);
+        if (nwin >= g.K && nwin <= 255 && hi > lo) {
+            const float invw = 7.0f / (hi - lo);
+            // ---- pass 1: histogram -------------------------------------------------------------
+            unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit
+            for (int lr = r0w; lr <= r1w; ++lr) {
+                const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                for (int i = a; i < e; ++i) {
+                    const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+                    const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                                        : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                    const int bk = bucket_of(d, lo, invw);
+                    const unsigned inc = 1u << ((bk & 3) << 3);
+                    hlo += bk < 4 ? inc : 0u;
+                    hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                }
+            }
+            int bstar = -1, below = 0, in_b = 0, cum = 0;
+#pragma unroll
+            for (int bk = 0; bk < 8; ++bk) {
+                const int cb = (int)(((bk < 4 ? hlo : hhi) >> ((bk & 3) << 3)) & 0xffu);
+                if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; in_b = cb; }
+                cum += cb;
+            }
+            if (bstar >= 0 && in_b <= kListCap) {
+                // ---- pass 2: accumulate sure members, collect the boundary bucket ----------------
+                int m = 0;
+                for (int lr = r0w; lr <= r1w; ++lr) {
+                    const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                    for (int i = a; i < e; ++i) {
+                        const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+                        const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                                            : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                        const int bk = bucket_of(d, lo, invw);
+                        if (bk < bstar) {
+                            if (FUSED) {
+                                const float2 f = s_fl[i];
+                                ay = __fadd_rn(ay, f.x);
+                                ax = __fadd_rn(ax, f.y);
+                            }
+                        } else if (bk == bstar) {
+                            s_ld[m][tid] = d;
+                            s_li[m][tid] = i;
+                            ++m;
+                        }
+                    }
+                }
+                // order the first `need` boundary candidates by (d, trajectory index)
+                const int need = g.K - below;
+                for (int t = 0; t < need; ++t) {
+                    int best = t;
+                    float bd = s_ld[t][tid];
+                    int bj = s_pj[s_li[t][tid]];
+                    for (int u = t + 1; u < m; ++u) {
+                        const float du = s_ld[u][tid];
+                        if (du < bd || (du == bd && s_pj[s_li[u][tid]] < bj)) {
+                            best = u;
+                            bd = du;
+                            bj = s_pj[s_li[u][tid]];
+                        }
+                    }
+                    const int ib = s_li[best][tid];
+                    if (best != t) {
+                        s_ld[best][tid] = s_ld[t][tid];
+                        s_li[best][tid] = s_li[t][tid];
+                        s_ld[t][tid] = bd;
+                        s_li[t][tid] = ib;
+                    }
+                    if (FUSED) {
+                        const float2 f = s_fl[ib];
+                        ay = __fadd_rn(ay, f.x);
+                        ax = __fadd_rn(ax, f.y);
+                    }
+                    t_d = bd;
+                    t_j = bj;
+                }
+                resolved = true;
             }
         }
     }
 
-    const int64_t c = (int64_t)iy * g.Wq + ix;
-    const int64_t sq = slab * g.q + c;
-    if (EMIT == 1) {
-        if (active) {
-            // heap sort: repeatedly move the current maximum to the end
-            for (int m = h.K - 1; m >= 0; --m) {
+    const int c = iy * g.Wq + ix;
+    const int64_t sq = (int64_t)slab * g.q + c;
+    if (active) {
+        if (resolved) {
+            tau[sq] = t_d;
+            jcut[sq] = t_j;
+            atomicMax(&blk_max, __float_as_uint(t_d));
+            if (FUSED) {
+                const float Kf = (float)g.K;
+                const float2 v = make_float2(__fdiv_rn(ay, Kf), __fdiv_rn(ax, Kf));     // torch.mean
+                reinterpret_cast<float2 *>(lut)[sq] = v;
+                if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
+            }
+        } else {
+            worklist[atomicAdd(work_count, 1)] = (int)sq;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tile_max[(int64_t)slab * gridDim.x + blockIdx.x] = blk_max;
+        if (blk_max != 0u) atomicMax(tau_max + slab, blk_max);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. work-list queries: ring search with the max-heap over the global cell list
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kKnnBlock)
+knn_heap_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
+                float *__restrict__ tau, int *__restrict__ jcut, unsigned *__restrict__ tau_max,
+                unsigned *__restrict__ tile_max, const int *__restrict__ worklist,
+                const int *__restrict__ work_count, int all_queries)
+{
+    extern __shared__ float heap_mem[];
+    const int tid = threadIdx.x;
+    const int64_t total = all_queries ? g.S * (int64_t)g.q : (int64_t)*work_count;
+    const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
+    const int tiles = tiles_x * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
+    for (int64_t w = (int64_t)blockIdx.x * kKnnBlock + tid; w < total; w += (int64_t)gridDim.x * kKnnBlock) {
+        const int64_t sq = all_queries ? w : (int64_t)worklist[w];
+        const int64_t slab = sq / g.q;
+        const Query q = make_query((int)(sq - slab * g.q), g);
+        const int *cstart = cell_start + slab * (g.NC + 1);
+        const float4 *sorted = sorted_all + slab * g.n;
+        Heap h;
+        h.hd = heap_mem + tid;
+        h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * kKnnBlock) + tid;
+        h.K = g.K;
+        h.cnt = 0;
+        h.rootd = INFINITY;
+        h.rootj = 0x7fffffff;
+        int r = g.r0;
+        auto ins = [&](float d, const float4 &rec) { h.consider(d, __float_as_int(rec.z)); };
+        scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, ins);
+        while (true) {
+            const float bnd = window_bound(q.cqy, q.cqx, r, g, q.qy, q.qx);
+            if (bnd == INFINITY) break;
+            if (h.cnt == h.K && h.rootd < bnd) break;      // strict: ties could still win on index
+            ++r;
+            scan_cells(cstart, sorted, q.cqy - r, q.cqx - r, q.cqx + r, g, q.qy, q.qx, ins);
+            scan_cells(cstart, sorted, q.cqy + r, q.cqx - r, q.cqx + r, g, q.qy, q.qx, ins);
+            for (int row = q.cqy - r + 1; row <= q.cqy + r - 1; ++row) {
+                scan_cells(cstart, sorted, row, q.cqx - r, q.cqx - r, g, q.qy, q.qx, ins);
+                scan_cells(cstart, sorted, row, q.cqx + r, q.cqx + r, g, q.qy, q.qx, ins);
+            }
+        }
+        tau[sq] = h.rootd;
+        jcut[sq] = h.rootj;
+        const unsigned bits = __float_as_uint(h.rootd);
+        atomicMax(tau_max + slab, bits);
+        atomicMax(tile_max + slab * tiles + (q.iy / kKnnTileH) * tiles_x + q.ix / kKnnTileW, bits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. generic accumulation from (tau, jcut): LUT for any R / iwd, flow_to_next, sorted index lists
+// ---------------------------------------------------------------------------------------------
+// what: bit 0 = LUT (+wsum), bit 1 = flow_to_next, bit 2 = sorted neighbour lists (test entry)
+__global__ void __launch_bounds__(kKnnBlock)
+lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restrict__ cell_start,
+                      const float4 *__restrict__ sorted_all, const float *__restrict__ tau,
+                      const int *__restrict__ jcut, int what, float *__restrict__ lut,
+                      float *__restrict__ lut_copy, float *__restrict__ f2n,
+                      float *__restrict__ wsum, int32_t *__restrict__ ind_out,
+                      float *__restrict__ dist_out, const int *__restrict__ worklist,
+                      const int *__restrict__ work_count, int all_queries)
+{
+    extern __shared__ float heap_mem[];
+    const int tid = threadIdx.x;
+    const int64_t total = all_queries ? g.S * (int64_t)g.q : (int64_t)*work_count;
+    for (int64_t w = (int64_t)blockIdx.x * kKnnBlock + tid; w < total; w += (int64_t)gridDim.x * kKnnBlock) {
+        const int64_t sq = all_queries ? w : (int64_t)worklist[w];
+        const int64_t slab = sq / g.q;
+        const int c = (int)(sq - slab * g.q);
+        const Query q = make_query(c, g);
+        const int *cstart = cell_start + slab * (g.NC + 1);
+        const float4 *sorted = sorted_all + slab * g.n;
+        const float t_d = tau[sq];
+        const int t_j = jcut[sq];
+        const int r = radius_for(t_d, q.cqy, q.cqx, g, q.qy, q.qx);
+        if (what & 4) {
+            Heap h;
+            h.hd = heap_mem + tid;
+            h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * kKnnBlock) + tid;
+            h.K = g.K;
+            h.cnt = 0;
+            h.rootd = INFINITY;
+            h.rootj = 0x7fffffff;
+            int members = 0;
+            scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                const int j = __float_as_int(rec.z);
+                if (d < t_d || (d == t_d && j <= t_j)) {
+                    if (members < g.K) h.consider(d, j);
+                    ++members;
+                }
+            });
+            for (int m = g.K - 1; m >= 0; --m) {
                 float d = h.D(0);
                 int j = h.J(0);
-                float ld = h.D(m);
-                int lj = h.J(m);
-                if (m > 0) h.sift_down(0, m, ld, lj);
+                if (members != g.K) { d = -1.0f; j = -1; }       // selection bug detector
+                else if (m > 0) h.sift_down(0, m, h.D(m), h.J(m));
                 ind_out[sq * g.K + m] = j;
                 if (dist_out) dist_out[sq * g.K + m] = d;
             }
+            continue;
         }
-        return;
-    }
-
-    if (active) {
         const int64_t b = slab / g.nb, bin = slab - b * g.nb;
         const float2 *tmid = slab_points(traj, g, slab);
-        tau[sq] = h.rootd;
-        jcut[sq] = h.rootj;
-        atomicMax(&blk_max, __float_as_uint(h.rootd));
-        float S = 0.0f;
-        if (g.iwd) {
-            for (int k = 0; k < g.K; ++k) S = __fadd_rn(S, __fdiv_rn(1.0f, __fadd_rn(h.D(k), kIwdEps)));
-            wsum[sq] = S;
-        }
         const float Kf = (float)g.K;
-        for (int r = 0; r < g.R; ++r) {
-            const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb) + r) * g.n;
-            float ay = 0.0f, ax = 0.0f;
-            for (int k = 0; k < g.K; ++k) {
-                int j = h.J(k);
-                float2 pr = __ldg(tref + j), pm = __ldg(tmid + j);
-                float fy = __fsub_rn(pr.x, pm.x), fx = __fsub_rn(pr.y, pm.y);     // focus.py:141
-                if (g.iwd) {
-                    float w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(h.D(k), kIwdEps)), S);
-                    fy = __fmul_rn(w, fy);
-                    fx = __fmul_rn(w, fx);
-                }
-                ay = __fadd_rn(ay, fy);
-                ax = __fadd_rn(ax, fx);
+        if (what & 1) {
+            float S = 1.0f;
+            if (g.iwd) {
+                S = 0.0f;
+                scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                    if (d < t_d || (d == t_d && __float_as_int(rec.z) <= t_j))
+                        S = __fadd_rn(S, __fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)));
+                });
+                wsum[sq] = S;
             }
-            if (!g.iwd) { ay = __fdiv_rn(ay, Kf); ax = __fdiv_rn(ax, Kf); }     // torch.mean
-            float2 v = make_float2(ay, ax);
-            reinterpret_cast<float2 *>(lut)[sq * g.R + r] = v;
-            if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq * g.R + r] = v;
+            for (int rr = 0; rr < g.R; ++rr) {
+                const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb) + rr) * g.n;
+                float ay = 0.0f, ax = 0.0f;
+                scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                    const int j = __float_as_int(rec.z);
+                    if (d < t_d || (d == t_d && j <= t_j)) {
+                        const float2 pr = __ldg(tref + j);
+                        float fy = __fsub_rn(pr.x, rec.x), fx = __fsub_rn(pr.y, rec.y);   // focus.py:141
+                        if (g.iwd) {
+                            const float wgt = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)), S);
+                            fy = __fmul_rn(wgt, fy);
+                            fx = __fmul_rn(wgt, fx);
+                        }
+                        ay = __fadd_rn(ay, fy);
+                        ax = __fadd_rn(ax, fx);
+                    }
+                });
+                if (!g.iwd) { ay = __fdiv_rn(ay, Kf); ax = __fdiv_rn(ax, Kf); }     // torch.mean
+                const float2 v = make_float2(ay, ax);
+                reinterpret_cast<float2 *>(lut)[sq * g.R + rr] = v;
+                if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq * g.R + rr] = v;
+            }
         }
-        if (f2n != nullptr && bin < g.nb - 1) {                     // focus.py:170-176
+        if ((what & 2) && bin < g.nb - 1) {                     // focus.py:170-176
             const float2 *tnext = tmid + g.n;
             float ay = 0.0f, ax = 0.0f;
-            for (int k = 0; k < g.K; ++k) {
-                int j = h.J(k);
-                float2 pn = __ldg(tnext + j), pm = __ldg(tmid + j);
-                ay = __fadd_rn(ay, __fsub_rn(pn.x, pm.x));
-                ax = __fadd_rn(ax, __fsub_rn(pn.y, pm.y));
-            }
+            scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                const int j = __float_as_int(rec.z);
+                if (d < t_d || (d == t_d && j <= t_j)) {
+                    const float2 pn = __ldg(tnext + j);
+                    ay = __fadd_rn(ay, __fsub_rn(pn.x, rec.x));
+                    ax = __fadd_rn(ax, __fsub_rn(pn.y, rec.y));
+                }
+            });
             reinterpret_cast<float2 *>(f2n)[(b * (g.nb - 1) + bin) * g.q + c] =
                 make_float2(__fdiv_rn(ay, Kf), __fdiv_rn(ax, Kf));
         }
     }
-    __syncthreads();
-    if (tid == 0 && blk_max != 0u) atomicMax(tau_max + slab, blk_max);
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. backward: gather d loss / d LUT into the trajectories
+// 5. backward: gather d loss / d LUT into the trajectories
 // ---------------------------------------------------------------------------------------------
 // dtraj[b, r, j]      =  sum_bins sum_{c : j in KNN(b,bin,c)} w(c,j) dLUT[b,bin,c,r]
 // dtraj[b, R+bin, j]  = -sum_r (same inner sum) [- / + the flow_to_next terms]
-template <int RT>   // RT = compile-time R (1) or 0 for the generic loop
+template <bool L1D, bool IWD, bool F2N, int RT>   // RT = compile-time R (1) or 0 = runtime R
 __global__ void __launch_bounds__(128)
 lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restrict__ tau,
                     const int *__restrict__ jcut, const float *__restrict__ wsum,
-                    const unsigned *__restrict__ tau_max, const float *__restrict__ dlut,
-                    const float *__restrict__ df2n, float *__restrict__ dtraj)
+                    const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
+                    const float *__restrict__ dlut, const float *__restrict__ df2n,
+                    float *__restrict__ dtraj)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
     if (j >= g.n) return;
     const int R = RT ? RT : g.R;
     float2 accr[RT ? RT : kMaxTref];
@@ -334,111 +650,224 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
     for (int r = 0; r < (RT ? RT : kMaxTref); ++r) accr[r] = make_float2(0.f, 0.f);
     float2 carry = make_float2(0.f, 0.f);
     const float invK = 1.0f / (float)g.K;
-    const float fs = (float)g.s;
-    float2 *dt = reinterpret_cast<float2 *>(dtraj) + b * (g.R + g.nb) * g.n;
+    const float fs = (float)g.s, inv_s = 1.0f / fs;
+    const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
+    const int tiles_y = (g.Hq + kKnnTileH - 1) / kKnnTileH;
+    const int Wq = g.Wq;
+    float2 *dt = reinterpret_cast<float2 *>(dtraj) + (int64_t)b * (g.R + g.nb) * g.n;
 
     for (int bin = 0; bin < g.nb; ++bin) {
-        const int64_t slab = b * g.nb + bin;
+        const int slab = b * g.nb + bin;
         const float2 p = slab_points(traj, g, slab)[j];
-        float tm = __uint_as_float(tau_max[slab]);
-        float rho = g.l1dist ? tm : sqrtf(tm);
-        rho = rho * 1.0001f + 1e-3f;
-        float2 mid = make_float2(0.f, 0.f);      // sum_r of this bin's gather
-        float2 nxt = make_float2(0.f, 0.f);      // flow_to_next gather of this bin
+        const float tm = __uint_as_float(__ldg(tau_max + slab));
+        float rho_g = L1D ? tm : sqrtf(tm);
+        rho_g = rho_g * 1.0001f + 1e-3f;
+        float2 nxt = make_float2(0.f, 0.f);
         float2 binr[RT ? RT : kMaxTref];
 #pragma unroll
         for (int r = 0; r < (RT ? RT : kMaxTref); ++r) binr[r] = make_float2(0.f, 0.f);
-        if (p.x == p.x && p.y == p.y && rho == rho) {
-            int iy0 = max(0, (int)floorf((p.x - rho - g.off) / fs));
-            int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) / fs));
-            int ix0 = max(0, (int)floorf((p.y - rho - g.off) / fs));
-            int ix1 = min(g.Wq - 1, (int)ceilf((p.y + rho - g.off) / fs));
-            for (int iy = iy0; iy <= iy1; ++iy) {
+        const float *tau_s = tau + (int64_t)slab * g.q;
+        const int *jcut_s = jcut + (int64_t)slab * g.q;
+        const float2 *dl_s = reinterpret_cast<const float2 *>(dlut) + (int64_t)slab * g.q * g.R;
+        const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
+                                 : nullptr;
+        const bool do_next = F2N && bin < g.nb - 1;
+        if (p.x == p.x && p.y == p.y && rho_g == rho_g) {
+            // local reach: the largest tau of any 16x8-query tile that can contain a query whose
+            // K-set holds p (tile rectangle closer to p than the tile's own reach)
+            const int ty0 = max(0, (int)floorf((p.x - rho_g - g.off) * inv_s)) / kKnnTileH;
+            const int ty1 = min(g.Hq - 1, max(0, (int)ceilf((p.x + rho_g - g.off) * inv_s))) / kKnnTileH;
+            const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
+            const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
+            const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
+            float rho = 0.0f;
+            for (int ty = ty0; ty <= ty1; ++ty) {
+                const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
+                const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
+                const float ddy = fmaxf(fmaxf(y_lo - p.x, p.x - y_hi), 0.0f);
+                for (int tx = tx0; tx <= tx1; ++tx) {
+                    const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
+                    const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
+                    const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
+                    const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
+                    const float reach = (L1D ? tmt : sqrtf(tmt)) * 1.0001f + 1e-3f;
+                    const float gap = L1D ? ddy + ddx : sqrtf(ddy * ddy + ddx * ddx);
+                    if (gap <= reach) rho = fmaxf(rho, reach);
+                }
+            }
+            const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
+            const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
+            const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
+            const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
+            const int nx = ix1 - ix0 + 1;
+            const float qx0 = __fadd_rn((float)(ix0 * g.s), g.off);
+            for (int iy = iy0; iy <= iy1 && nx > 0; ++iy) {
                 const float qy = __fadd_rn((float)(iy * g.s), g.off);
-                for (int ix = ix0; ix <= ix1; ++ix) {
-                    const float qx = __fadd_rn((float)(ix * g.s), g.off);
-                    const float d = knn_dist(qy, qx, p.x, p.y, g.l1dist);
-                    const int64_t sq = slab * g.q + (int64_t)iy * g.Wq + ix;
-                    const float tc = __ldg(tau + sq);
-                    if (d < tc || (d == tc && (int)j <= __ldg(jcut + sq))) {
-                        float w = invK;
-                        if (g.iwd)
-                            w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)), __ldg(wsum + sq));
-                        const float2 *dl = reinterpret_cast<const float2 *>(dlut) + sq * g.R;
+                const float dy = __fsub_rn(qy, p.x);
+                const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
+                const int o = iy * Wq + ix0;
+                const float *tp = tau_s + o;
+                float qx = qx0;                       // exact: lattice coordinates are multiples of 0.5
+#pragma unroll 4
+                for (int k = 0; k < nx; ++k, qx += fs) {
+                    const float dx = __fsub_rn(qx, p.y);
+                    const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
+                    const float tc = __ldg(tp + k);
+                    if (d <= tc) {
+                        if (d < tc || j <= __ldg(jcut_s + o + k)) {
+                            float w = 1.0f;
+                            if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
+                                                    __ldg(wsum + (int64_t)slab * g.q + o + k));
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            float2 v = __ldg(dl + r);
-                            binr[r].x += w * v.x;
-                            binr[r].y += w * v.y;
-                        }
-                        if (df2n != nullptr && bin < g.nb - 1) {
-                            float2 v = __ldg(reinterpret_cast<const float2 *>(df2n) +
-                                             (b * (g.nb - 1) + bin) * g.q + (int64_t)iy * g.Wq + ix);
-                            nxt.x += invK * v.x;
-                            nxt.y += invK * v.y;
+                            for (int r = 0; r < R; ++r) {
+                                const float2 v = __ldg(dl_s + (o + k) * R + r);
+                                binr[r].x += w * v.x;
+                                binr[r].y += w * v.y;
+                            }
+                            if (do_next) {
+                                const float2 v = __ldg(dn_s + o + k);
+                                nxt.x += v.x;
+                                nxt.y += v.y;
+                            }
                         }
                     }
                 }
             }
         }
+        float2 mid = make_float2(0.f, 0.f);      // sum_r of this bin's gather
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+            if (!IWD) { binr[r].x *= invK; binr[r].y *= invK; }     // mean: one scale per bin
             accr[r].x += binr[r].x;
             accr[r].y += binr[r].y;
             mid.x += binr[r].x;
             mid.y += binr[r].y;
         }
-        dt[(g.R + bin) * g.n + j] = make_float2(-mid.x - nxt.x + carry.x, -mid.y - nxt.y + carry.y);
+        nxt.x *= invK;
+        nxt.y *= invK;
+        dt[(int64_t)(g.R + bin) * g.n + j] = make_float2(-mid.x - nxt.x + carry.x, -mid.y - nxt.y + carry.y);
         carry = nxt;
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) dt[r * g.n + j] = accr[r];
+    for (int r = 0; r < R; ++r) dt[(int64_t)r * g.n + j] = accr[r];
 }
 
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+const int *g_last_work_count = nullptr;     // inspection hook (cmax_last_worklist_count)
+
+template <bool L1D, bool FUSED>
+static void launch_fast(const Geom &g, dim3 grid, cudaStream_t st, const int *cell_start,
+                        const float4 *sorted, const float2 *sflow, float *lut, float *lut_copy,
+                        float *tau, int *jcut, unsigned *tau_max, unsigned *tile_max, int *worklist,
+                        int *work_count)
+{
+    knn_fast_kernel<L1D, FUSED><<<grid, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, lut, lut_copy,
+                                                            tau, jcut, tau_max, tile_max, worklist,
+                                                            work_count);
+}
+
 int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,
                        float *flow_lut_out, int32_t *ind_out, float *dist_out, cudaStream_t st)
 {
     int *cell_start = reinterpret_cast<int *>(ws + L.cell_start);
     float4 *sorted = reinterpret_cast<float4 *>(ws + L.sorted);
-    size_t smem_bin = (size_t)g.NC * sizeof(int);
+    float2 *sflow = reinterpret_cast<float2 *>(ws + L.sflow);
+    float *tau = reinterpret_cast<float *>(ws + L.tau);
+    int *jcut = reinterpret_cast<int *>(ws + L.jcut);
+    unsigned *tau_max = reinterpret_cast<unsigned *>(ws + L.tau_max);
+    unsigned *tile_max = reinterpret_cast<unsigned *>(ws + L.tile_max);
+    int *worklist = reinterpret_cast<int *>(ws + L.worklist);
+    int *work_count = reinterpret_cast<int *>(ws + L.work_count);
+    g_last_work_count = work_count;
+    float *lut = reinterpret_cast<float *>(ws + L.lut);
+    const size_t smem_bin = (size_t)g.NC * sizeof(int);
+    const size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kMaxCells * (int)sizeof(int));
-        cudaFuncSetAttribute(knn_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(knn_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kMaxKnn * kKnnBlock * 8);
-        cudaFuncSetAttribute(knn_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(lut_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kMaxKnn * kKnnBlock * 8);
         attr_done = true;
     }
+    const bool test_entry = ind_out != nullptr;
+    const bool fused = !test_entry && g.R == 1 && !g.iwd;
     {
         StageScope sc(ST_BIN_POINTS, st);
-        bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, cell_start, sorted);
+        bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, cell_start, sorted,
+                                                                 fused ? sflow : nullptr);
         count_launch();
     }
     const int tiles = ((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
     dim3 grid(tiles, (unsigned)g.S);
-    size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
     StageScope sc(ST_KNN_SELECT, st);
-    count_launch();
-    if (ind_out != nullptr) {
-        knn_select_kernel<1><<<grid, kKnnBlock, smem_heap, st>>>(
-            traj, g, cell_start, sorted, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-            nullptr, ind_out, dist_out);
+    cudaMemsetAsync(tau_max, 0, sizeof(unsigned) * g.S, st);
+    cudaMemsetAsync(work_count, 0, sizeof(int), st);
+    // the staged fast path needs the window to fit the static tables and S*q to fit an int
+    const bool can_fast = g.r_fast <= 10 && g.S * (int64_t)g.q < (int64_t)INT32_MAX;
+    const int heap_grid = 148 * 4;
+    if (can_fast) {
+        float *lc = fused ? flow_lut_out : nullptr;
+        if (g.l1dist) {
+            if (fused) launch_fast<true, true>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
+            else launch_fast<true, false>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
+        } else {
+            if (fused) launch_fast<false, true>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
+            else launch_fast<false, false>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
+        }
+        knn_heap_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(g, cell_start, sorted, tau, jcut, tau_max,
+                                                               tile_max, worklist, work_count, 0);
+        count_launch(2);
+    } else {
+        cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
+        knn_heap_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(g, cell_start, sorted, tau, jcut, tau_max,
+                                                               tile_max, worklist, work_count, 1);
+        count_launch();
+    }
+    if (test_entry) {
+        lut_accumulate_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(
+            traj, g, cell_start, sorted, tau, jcut, 4, nullptr, nullptr, nullptr, nullptr, ind_out,
+            dist_out, worklist, work_count, 1);
+        count_launch();
         return check_launch();
     }
-    unsigned *tau_max = reinterpret_cast<unsigned *>(ws + L.tau_max);
-    cudaMemsetAsync(tau_max, 0, sizeof(unsigned) * g.S, st);
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
-    knn_select_kernel<0><<<grid, kKnnBlock, smem_heap, st>>>(
-        traj, g, cell_start, sorted, reinterpret_cast<float *>(ws + L.lut),
-        want_next ? reinterpret_cast<float *>(ws + L.f2n) : nullptr,
-        reinterpret_cast<float *>(ws + L.tau), reinterpret_cast<int *>(ws + L.jcut),
-        reinterpret_cast<float *>(ws + L.wsum), tau_max, flow_lut_out, nullptr, nullptr);
+    float *f2n = reinterpret_cast<float *>(ws + L.f2n);
+    float *wsum = reinterpret_cast<float *>(ws + L.wsum);
+    if (fused && can_fast) {
+        // LUT of the work-list queries; flow_to_next (if any) for everybody
+        lut_accumulate_kernel<<<heap_grid, kKnnBlock, 0, st>>>(
+            traj, g, cell_start, sorted, tau, jcut, 1, lut, flow_lut_out, nullptr, wsum, nullptr, nullptr,
+            worklist, work_count, 0);
+        count_launch();
+        if (want_next) {
+            lut_accumulate_kernel<<<heap_grid * 4, kKnnBlock, 0, st>>>(
+                traj, g, cell_start, sorted, tau, jcut, 2, nullptr, nullptr, f2n, wsum, nullptr, nullptr,
+                worklist, work_count, 1);
+            count_launch();
+        }
+    } else {
+        lut_accumulate_kernel<<<heap_grid * 4, kKnnBlock, 0, st>>>(
+            traj, g, cell_start, sorted, tau, jcut, 1 | (want_next ? 2 : 0), lut, flow_lut_out, f2n, wsum,
+            nullptr, nullptr, worklist, work_count, 1);
+        count_launch();
+    }
     return check_launch();
+}
+
+template <bool L1D, bool IWD, bool F2N>
+static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *traj, const float *tau,
+                       const int *jcut, const float *wsum, const unsigned *tmax,
+                       const unsigned *tile_max, const float *dlut, const float *df2n, float *dtraj)
+{
+    if (g.R == 1)
+        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj);
+    else
+        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj);
 }
 
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
@@ -450,14 +879,22 @@ int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char 
     const int *jcut = reinterpret_cast<const int *>(ws + L.jcut);
     const float *wsum = reinterpret_cast<const float *>(ws + L.wsum);
     const unsigned *tmax = reinterpret_cast<const unsigned *>(ws + L.tau_max);
+    const unsigned *tile_max = reinterpret_cast<const unsigned *>(ws + L.tile_max);
     StageScope sc(ST_LUT_BWD, st);
     count_launch();
     const float *dlut = reinterpret_cast<const float *>(ws + L.dlut);
-    const float *df2n = want_next ? reinterpret_cast<const float *>(ws + L.df2n) : nullptr;
-    if (g.R == 1)
-        lut_backward_kernel<1><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, dlut, df2n, dtraj);
-    else
-        lut_backward_kernel<0><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, dlut, df2n, dtraj);
+    const float *df2n = reinterpret_cast<const float *>(ws + L.df2n);
+    const int key = (g.l1dist ? 4 : 0) | (g.iwd ? 2 : 0) | (want_next ? 1 : 0);
+    switch (key) {
+    case 0: launch_bwd<false, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 1: launch_bwd<false, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 2: launch_bwd<false, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 3: launch_bwd<false, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 4: launch_bwd<true, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 5: launch_bwd<true, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 6: launch_bwd<true, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    default: launch_bwd<true, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    }
     return check_launch();
 }
 

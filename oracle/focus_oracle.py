@@ -403,8 +403,8 @@ class FocusOracle:
         dt_ = self.dtype
         H, W = self.image_shape
         s, K, R = self.lut_superpixel_size, self.num_knn, self.num_tref
-        traj32 = np.asarray(trajectories, np.float32)
-        traj = traj32.astype(dt_)
+        traj32 = np.asarray(trajectories, np.float32)        # integer decisions (KNN) use float32
+        traj = np.asarray(trajectories).astype(dt_)          # float math keeps the caller's precision
         times32 = np.asarray(times, np.float32)
         ev32 = np.asarray(events, np.float32)
         B, n_t, n, _ = traj.shape
