@@ -200,6 +200,22 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# multi-rank plumbing (no collective on the data path: windows are sharded, ranks independent)
+# ------------------------------------------------------------------------------------------
+def aggregate_over_ranks(ms_total, ms_e2e, n_valid, n_rows, dist, device):
+    """Whole-job numbers: time = MAX over ranks, work = SUM over ranks (weak scaling).
+    `dist` is torch.distributed (initialised) or None for a single process."""
+    t = torch.tensor([ms_total, ms_e2e, float(n_valid), float(n_rows)], device=device,
+                     dtype=torch.float64)
+    if dist is None:
+        return ms_total, ms_e2e, float(n_valid), float(n_rows)
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    return tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -308,16 +324,7 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- max over ranks -----------------------------------------------------------------------
-    t = torch.tensor([ms_total, ms_e2e, float(n_valid), float(B * M)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total, ms_e2e = tmax[0].item(), tmax[1].item()
-        ev_all, rows_all = tsum[2].item(), tsum[3].item()
-    else:
-        ev_all, rows_all = float(n_valid), float(B * M)
+    ms_total, ms_e2e, ev_all, rows_all = aggregate_over_ranks(ms_total, ms_e2e, n_valid, B * M, dist, dev)
 
     if rank == 0:
         ms_step = ms_total / args.steps
