@@ -105,7 +105,7 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     if (c->num_knn > n) return CMAX_ERR_BAD_SHAPE;
     if (c->polarity_aware_batching && (npos < 0 || npos > M)) return CMAX_ERR_BAD_SHAPE;
     if (c->num_knn > kMaxKnn || c->num_tref > kMaxTref) return CMAX_ERR_UNSUPPORTED;
-    if (B > 65535 || n > (int64_t)INT32_MAX / 2 || B * c->num_bins > (int64_t)INT32_MAX)
+    if (B > 65535 || c->num_bins > 65535 || n > (int64_t)INT32_MAX / 2 || B * c->num_bins > (int64_t)INT32_MAX)
         return CMAX_ERR_UNSUPPORTED;
     memset(g, 0, sizeof(*g));
     knn_geom(c->height, c->width, c->lut_superpixel_size, n, c->num_knn, g);
@@ -180,6 +180,7 @@ Layout make_layout(const Geom &g)
     L.focus_partials = take(sizeof(double) * L.n_img_blocks);
     L.smooth_partials = take(sizeof(double) * (L.n_sm_blocks > 0 ? L.n_sm_blocks : 1));
     take_knn(g, L, take);
+    L.bpart = take(sizeof(float2) * g.S * g.n * (g.R + (g.smooth_next ? 1 : 0)));
     L.lut = take(sizeof(float) * nlut);
     L.f2n = take(sizeof(float) * (nf2n > 0 ? nf2n : 4));
     L.raw = take(sizeof(float) * npix);

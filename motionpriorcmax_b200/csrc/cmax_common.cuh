@@ -52,7 +52,7 @@ struct Header {               // first 1 KiB of the workspace
 
 struct Layout {
     size_t header, focus_partials, smooth_partials, cell_start, sorted, sflow, tau, jcut, wsum,
-        tau_max, tile_max, worklist, work_count, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
+        tau_max, tile_max, worklist, work_count, bpart, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
     int n_img_blocks, n_sm_blocks;
 };
 

@@ -633,123 +633,147 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
 // ---------------------------------------------------------------------------------------------
 // dtraj[b, r, j]      =  sum_bins sum_{c : j in KNN(b,bin,c)} w(c,j) dLUT[b,bin,c,r]
 // dtraj[b, R+bin, j]  = -sum_r (same inner sum) [- / + the flow_to_next terms]
+// Stage A: one thread per (sample, bin, trajectory) gathers this bin's contribution;
+// stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
+// fixed order -> deterministic, and 15x more threads in flight for the latency-bound gather.
 template <bool L1D, bool IWD, bool F2N, int RT>   // RT = compile-time R (1) or 0 = runtime R
 __global__ void __launch_bounds__(128)
 lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restrict__ tau,
                     const int *__restrict__ jcut, const float *__restrict__ wsum,
                     const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
                     const float *__restrict__ dlut, const float *__restrict__ df2n,
-                    float *__restrict__ dtraj)
+                    float2 *__restrict__ part)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int bin = blockIdx.y;
+    const int b = blockIdx.z;
     if (j >= g.n) return;
     const int R = RT ? RT : g.R;
-    float2 accr[RT ? RT : kMaxTref];
-#pragma unroll
-    for (int r = 0; r < (RT ? RT : kMaxTref); ++r) accr[r] = make_float2(0.f, 0.f);
-    float2 carry = make_float2(0.f, 0.f);
     const float invK = 1.0f / (float)g.K;
     const float fs = (float)g.s, inv_s = 1.0f / fs;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int tiles_y = (g.Hq + kKnnTileH - 1) / kKnnTileH;
     const int Wq = g.Wq;
-    float2 *dt = reinterpret_cast<float2 *>(dtraj) + (int64_t)b * (g.R + g.nb) * g.n;
-
-    for (int bin = 0; bin < g.nb; ++bin) {
-        const int slab = b * g.nb + bin;
-        const float2 p = slab_points(traj, g, slab)[j];
-        const float tm = __uint_as_float(__ldg(tau_max + slab));
-        float rho_g = L1D ? tm : sqrtf(tm);
-        rho_g = rho_g * 1.0001f + 1e-3f;
-        float2 nxt = make_float2(0.f, 0.f);
-        float2 binr[RT ? RT : kMaxTref];
+    const int slab = b * g.nb + bin;
+    const float2 p = slab_points(traj, g, slab)[j];
+    const float tm = __uint_as_float(__ldg(tau_max + slab));
+    float rho_g = L1D ? tm : sqrtf(tm);
+    rho_g = rho_g * 1.0001f + 1e-3f;
+    float2 nxt = make_float2(0.f, 0.f);
+    float2 binr[RT ? RT : kMaxTref];
 #pragma unroll
-        for (int r = 0; r < (RT ? RT : kMaxTref); ++r) binr[r] = make_float2(0.f, 0.f);
-        const float *tau_s = tau + (int64_t)slab * g.q;
-        const int *jcut_s = jcut + (int64_t)slab * g.q;
-        const float2 *dl_s = reinterpret_cast<const float2 *>(dlut) + (int64_t)slab * g.q * g.R;
-        const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
-                                 : nullptr;
-        const bool do_next = F2N && bin < g.nb - 1;
-        if (p.x == p.x && p.y == p.y && rho_g == rho_g) {
-            // local reach: the largest tau of any 16x8-query tile that can contain a query whose
-            // K-set holds p (tile rectangle closer to p than the tile's own reach)
-            const int ty0 = max(0, (int)floorf((p.x - rho_g - g.off) * inv_s)) / kKnnTileH;
-            const int ty1 = min(g.Hq - 1, max(0, (int)ceilf((p.x + rho_g - g.off) * inv_s))) / kKnnTileH;
-            const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
-            const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
-            const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
-            float rho = 0.0f;
-            for (int ty = ty0; ty <= ty1; ++ty) {
-                const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
-                const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
-                const float ddy = fmaxf(fmaxf(y_lo - p.x, p.x - y_hi), 0.0f);
-                for (int tx = tx0; tx <= tx1; ++tx) {
-                    const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
-                    const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
-                    const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
-                    const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
-                    const float reach = (L1D ? tmt : sqrtf(tmt)) * 1.0001f + 1e-3f;
-                    const float gap = L1D ? ddy + ddx : sqrtf(ddy * ddy + ddx * ddx);
-                    if (gap <= reach) rho = fmaxf(rho, reach);
-                }
+    for (int r = 0; r < (RT ? RT : kMaxTref); ++r) binr[r] = make_float2(0.f, 0.f);
+    const float *tau_s = tau + (int64_t)slab * g.q;
+    const int *jcut_s = jcut + (int64_t)slab * g.q;
+    const float2 *dl_s = reinterpret_cast<const float2 *>(dlut) + (int64_t)slab * g.q * g.R;
+    const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
+                             : nullptr;
+    const bool do_next = F2N && bin < g.nb - 1;
+    if (p.x == p.x && p.y == p.y && rho_g == rho_g) {
+        // local reach: the largest tau of any 16x8-query tile that can contain a query whose
+        // K-set holds p (tile rectangle closer to p than the tile's own reach)
+        const int ty0 = max(0, (int)floorf((p.x - rho_g - g.off) * inv_s)) / kKnnTileH;
+        const int ty1 = min(g.Hq - 1, max(0, (int)ceilf((p.x + rho_g - g.off) * inv_s))) / kKnnTileH;
+        const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
+        const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
+        const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
+        float rho = 0.0f;
+        for (int ty = ty0; ty <= ty1; ++ty) {
+            const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
+            const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
+            const float ddy = fmaxf(fmaxf(y_lo - p.x, p.x - y_hi), 0.0f);
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
+                const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
+                const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
+                const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
+                const float reach = (L1D ? tmt : sqrtf(tmt)) * 1.0001f + 1e-3f;
+                const float gap = L1D ? ddy + ddx : sqrtf(ddy * ddy + ddx * ddx);
+                if (gap <= reach) rho = fmaxf(rho, reach);
             }
-            const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
-            const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
-            const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
-            const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
-            const int nx = ix1 - ix0 + 1;
-            const float qx0 = __fadd_rn((float)(ix0 * g.s), g.off);
-            for (int iy = iy0; iy <= iy1 && nx > 0; ++iy) {
-                const float qy = __fadd_rn((float)(iy * g.s), g.off);
-                const float dy = __fsub_rn(qy, p.x);
-                const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
-                const int o = iy * Wq + ix0;
-                const float *tp = tau_s + o;
-                float qx = qx0;                       // exact: lattice coordinates are multiples of 0.5
+        }
+        const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
+        const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
+        const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
+        const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
+        const int nx = ix1 - ix0 + 1;
+        const float qx0 = __fadd_rn((float)(ix0 * g.s), g.off);
+        for (int iy = iy0; iy <= iy1 && nx > 0; ++iy) {
+            const float qy = __fadd_rn((float)(iy * g.s), g.off);
+            const float dy = __fsub_rn(qy, p.x);
+            const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
+            const int o = iy * Wq + ix0;
+            const float *tp = tau_s + o;
+            float qx = qx0;                       // exact: lattice coordinates are multiples of 0.5
 #pragma unroll 4
-                for (int k = 0; k < nx; ++k, qx += fs) {
-                    const float dx = __fsub_rn(qx, p.y);
-                    const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
-                    const float tc = __ldg(tp + k);
-                    if (d <= tc) {
-                        if (d < tc || j <= __ldg(jcut_s + o + k)) {
-                            float w = 1.0f;
-                            if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
-                                                    __ldg(wsum + (int64_t)slab * g.q + o + k));
+            for (int k = 0; k < nx; ++k, qx += fs) {
+                const float dx = __fsub_rn(qx, p.y);
+                const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
+                const float tc = __ldg(tp + k);
+                if (d <= tc) {
+                    if (d < tc || j <= __ldg(jcut_s + o + k)) {
+                        float w = 1.0f;
+                        if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
+                                                __ldg(wsum + (int64_t)slab * g.q + o + k));
 #pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                const float2 v = __ldg(dl_s + (o + k) * R + r);
-                                binr[r].x += w * v.x;
-                                binr[r].y += w * v.y;
-                            }
-                            if (do_next) {
-                                const float2 v = __ldg(dn_s + o + k);
-                                nxt.x += v.x;
-                                nxt.y += v.y;
-                            }
+                        for (int r = 0; r < R; ++r) {
+                            const float2 v = __ldg(dl_s + (o + k) * R + r);
+                            binr[r].x += w * v.x;
+                            binr[r].y += w * v.y;
+                        }
+                        if (do_next) {
+                            const float2 v = __ldg(dn_s + o + k);
+                            nxt.x += v.x;
+                            nxt.y += v.y;
                         }
                     }
                 }
             }
         }
-        float2 mid = make_float2(0.f, 0.f);      // sum_r of this bin's gather
+    }
+    const int stride = R + (F2N ? 1 : 0);
+    float2 *out = part + ((int64_t)slab * g.n + j) * stride;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (!IWD) { binr[r].x *= invK; binr[r].y *= invK; }     // mean: one scale per bin
-            accr[r].x += binr[r].x;
-            accr[r].y += binr[r].y;
-            mid.x += binr[r].x;
-            mid.y += binr[r].y;
+    for (int r = 0; r < R; ++r) {
+        if (!IWD) { binr[r].x *= invK; binr[r].y *= invK; }     // mean: one scale per bin
+        out[r] = binr[r];
+    }
+    if (F2N) out[R] = make_float2(nxt.x * invK, nxt.y * invK);
+}
+
+__global__ void __launch_bounds__(128)
+lut_backward_assemble_kernel(Geom g, const float2 *__restrict__ part, int has_next,
+                             float *__restrict__ dtraj)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= g.n) return;
+    const int R = g.R, stride = R + (has_next ? 1 : 0);
+    float2 accr[kMaxTref];
+#pragma unroll
+    for (int r = 0; r < kMaxTref; ++r) accr[r] = make_float2(0.f, 0.f);
+    float2 carry = make_float2(0.f, 0.f);
+    float2 *dt = reinterpret_cast<float2 *>(dtraj) + (int64_t)b * (g.R + g.nb) * g.n;
+    for (int bin = 0; bin < g.nb; ++bin) {
+        const float2 *in = part + ((int64_t)(b * g.nb + bin) * g.n + j) * stride;
+        float2 mid = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kMaxTref; ++r) {
+            if (r < R) {
+                const float2 v = __ldg(in + r);
+                accr[r].x += v.x;
+                accr[r].y += v.y;
+                mid.x += v.x;
+                mid.y += v.y;
+            }
         }
-        nxt.x *= invK;
-        nxt.y *= invK;
+        const float2 nxt = has_next ? __ldg(in + R) : make_float2(0.f, 0.f);
         dt[(int64_t)(g.R + bin) * g.n + j] = make_float2(-mid.x - nxt.x + carry.x, -mid.y - nxt.y + carry.y);
         carry = nxt;
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) dt[(int64_t)r * g.n + j] = accr[r];
+    for (int r = 0; r < kMaxTref; ++r)
+        if (r < R) dt[(int64_t)r * g.n + j] = accr[r];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,39 +886,42 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
 template <bool L1D, bool IWD, bool F2N>
 static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *traj, const float *tau,
                        const int *jcut, const float *wsum, const unsigned *tmax,
-                       const unsigned *tile_max, const float *dlut, const float *df2n, float *dtraj)
+                       const unsigned *tile_max, const float *dlut, const float *df2n, float2 *part)
 {
     if (g.R == 1)
-        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj);
+        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
     else
-        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj);
+        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
 }
 
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
                         float *dtraj, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.n + 127) / 128), (unsigned)g.B);
+    dim3 grid((unsigned)((g.n + 127) / 128), (unsigned)g.nb, (unsigned)g.B);
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
+    float2 *dtraj_part = reinterpret_cast<float2 *>(ws + L.bpart);
     const float *tau = reinterpret_cast<const float *>(ws + L.tau);
     const int *jcut = reinterpret_cast<const int *>(ws + L.jcut);
     const float *wsum = reinterpret_cast<const float *>(ws + L.wsum);
     const unsigned *tmax = reinterpret_cast<const unsigned *>(ws + L.tau_max);
     const unsigned *tile_max = reinterpret_cast<const unsigned *>(ws + L.tile_max);
     StageScope sc(ST_LUT_BWD, st);
-    count_launch();
+    count_launch(2);
     const float *dlut = reinterpret_cast<const float *>(ws + L.dlut);
     const float *df2n = reinterpret_cast<const float *>(ws + L.df2n);
     const int key = (g.l1dist ? 4 : 0) | (g.iwd ? 2 : 0) | (want_next ? 1 : 0);
     switch (key) {
-    case 0: launch_bwd<false, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 1: launch_bwd<false, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 2: launch_bwd<false, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 3: launch_bwd<false, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 4: launch_bwd<true, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 5: launch_bwd<true, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    case 6: launch_bwd<true, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
-    default: launch_bwd<true, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj); break;
+    case 0: launch_bwd<false, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 1: launch_bwd<false, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 2: launch_bwd<false, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 3: launch_bwd<false, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 4: launch_bwd<true, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 5: launch_bwd<true, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 6: launch_bwd<true, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    default: launch_bwd<true, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
     }
+    dim3 grid2((unsigned)((g.n + 127) / 128), (unsigned)g.B);
+    lut_backward_assemble_kernel<<<grid2, 128, 0, st>>>(g, dtraj_part, want_next ? 1 : 0, dtraj);
     return check_launch();
 }
 
