@@ -12,6 +12,7 @@ int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStre
 int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
                 cudaStream_t st);
 extern const int *g_last_work_count;
+extern int g_last_work_bins;
 
 // ---------------------------------------------------------------------------------------------
 // stage timing / launch counting (single-threaded caller per process, like the reference)
@@ -85,7 +86,7 @@ void knn_geom(int H, int W, int s, int64_t n, int K, Geom *g)
     double rk = sqrt((double)K / (3.14159265358979 * (dens > 0 ? dens : 1e-9)));
     int r0 = (int)ceil((rk - 0.5 * g->cs) / g->cs);
     g->r0 = r0 < 0 ? 0 : (r0 > 8 ? 8 : r0);
-    g->r_fast = g->r0 + 1;
+    g->r_fast = g->r0 + 2;
 }
 
 int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos, Geom *g)
@@ -141,7 +142,7 @@ static void take_knn(const Geom &g, Layout &L, Take &take)
     L.tau_max = take(sizeof(unsigned) * g.S);
     L.tile_max = take(sizeof(unsigned) * g.S * tiles);
     L.worklist = take(sizeof(int) * g.S * g.q);
-    L.work_count = take(sizeof(int));
+    L.work_count = take(sizeof(int) * g.nb);
 }
 
 Layout make_knn_layout(const Geom &g)
@@ -569,11 +570,14 @@ int64_t cmax_launch_count(void) { return g_launches; }
 
 int64_t cmax_last_worklist_count(void *stream)
 {
-    if (!g_last_work_count) return -1;
-    int v = 0;
+    if (!g_last_work_count || g_last_work_bins <= 0 || g_last_work_bins > 65536) return -1;
+    static int host_counts[65536];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemcpyAsync(&v, g_last_work_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(host_counts, g_last_work_count, sizeof(int) * g_last_work_bins,
+                        cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    int64_t v = 0;
+    for (int i = 0; i < g_last_work_bins; ++i) v += host_counts[i];
     return v;
 }
 

@@ -264,10 +264,12 @@ __device__ __forceinline__ Query make_query(int c, const Geom &g)
 // ---------------------------------------------------------------------------------------------
 // 2. fast path
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 1280;    // points staged per CTA
-constexpr int kListCap = 12;       // boundary-bucket candidates kept per thread
+constexpr int kStageCap = 1024;    // points staged per CTA
+constexpr int kListCap = 20;       // boundary candidates kept per thread
 constexpr int kWinRows = kKnnTileH + 2 * 10;
 constexpr int kWinCols = kKnnTileW + 2 * 10;
+constexpr float kGuessLo = 0.82f;  // bracket around the previous bin's K-th key
+constexpr float kGuessHi = 1.22f;
 
 // bucket 0: d < lo; buckets 1..7: seven slices of [lo, hi); 8: d >= hi (not counted)
 __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
@@ -276,13 +278,19 @@ __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
     return d < lo ? 0 : min(__float2int_rd(v) + 1, 8);
 }
 
-template <bool L1D, bool FUSED>
+// GUESS = false: self-contained two-pass histogram select (first bin of a sample).
+// GUESS = true : the K-th key of the same LUT cell in the previous time bin brackets this
+//                bin's key (trajectories move smoothly between bins): ONE pass counts / accumulates
+//                everything below the bracket and lists the few candidates inside it.  A miss
+//                (bracket wrong, list full) sends the cell to the work list - never a wrong answer.
+template <bool L1D, bool FUSED, bool GUESS>
 __global__ void __launch_bounds__(kKnnBlock)
-knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
-                const float2 *__restrict__ sflow_all, float *__restrict__ lut,
-                float *__restrict__ lut_copy, float *__restrict__ tau, int *__restrict__ jcut,
-                unsigned *__restrict__ tau_max, unsigned *__restrict__ tile_max,
-                int *__restrict__ worklist, int *__restrict__ work_count)
+knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
+                const float4 *__restrict__ sorted_all, const float2 *__restrict__ sflow_all,
+                float *__restrict__ lut, float *__restrict__ lut_copy, float *__restrict__ tau,
+                int *__restrict__ jcut, unsigned *__restrict__ tau_max,
+                unsigned *__restrict__ tile_max, int *__restrict__ worklist,
+                int *__restrict__ work_count)
 {
     __shared__ float s_py[kStageCap], s_px[kStageCap];
     __shared__ int s_pj[kStageCap];
@@ -294,7 +302,7 @@ knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
     __shared__ unsigned blk_max;
 
     const int tid = threadIdx.x;
-    const int slab = blockIdx.y;
+    const int slab = blockIdx.y * g.nb + bin;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
@@ -349,52 +357,73 @@ knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
     }
     __syncthreads();
 
+    const int c = iy * g.Wq + ix;
+    const int64_t sq = (int64_t)slab * g.q + c;
     bool resolved = false;
     float t_d = 0.0f;
     int t_j = 0;
     float ay = 0.0f, ax = 0.0f;
+    int m = 0, need = 0;
     if (active && staged) {
         const float qy = __fadd_rn((float)(iy * g.s), g.off);
         const float qx = __fadd_rn((float)(ix * g.s), g.off);
         const int cqy = min((int)floorf(qy * g.inv_cs), g.Hc - 1);
         const int cqx = min((int)floorf(qx * g.inv_cs), g.Wc - 1);
-        const int r0w = max(cqy - r, 0) - wy0, r1w = min(cqy + r, g.Hc - 1) - wy0;
-        const int c0w = max(cqx - r, 0) - wx0, c1w = min(cqx + r, g.Wc - 1) - wx0 + 1;
         const float bnd = window_bound(cqy, cqx, r, g, qy, qx);
-        int nwin = 0;
-        for (int lr = r0w; lr <= r1w; ++lr) nwin += s_cell[lr][c1w] - s_cell[lr][c0w];
-        // density-based estimate of the K-th key and the histogram bracket around it
-        const float area = (float)((r1w - r0w + 1) * (c1w - c0w)) * g.cs * g.cs;
-        float est = (float)g.K * area / (3.14159265f * (float)max(nwin, 1));
-        if (L1D) est = sqrtf(est * 1.5707963f);        // l1 ball of radius t has area 2 t^2
-        const float lo = 0.45f * est;
-        const float hi = fminf(1.7f * est, bnd);
-        if (nwin >= g.K && nwin <= 255 && hi > lo) {
-            const float invw = 7.0f / (hi - lo);
-            // ---- pass 1: histogram -------------------------------------------------------------
-            unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit
-            for (int lr = r0w; lr <= r1w; ++lr) {
-                const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
-                for (int i = a; i < e; ++i) {
-                    const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
-                    const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
-                                        : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
-                    const int bk = bucket_of(d, lo, invw);
-                    const unsigned inc = 1u << ((bk & 3) << 3);
-                    hlo += bk < 4 ? inc : 0u;
-                    hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+        if (GUESS) {
+            // K-th key of the same cell in the previous bin as left by the *fast* kernel (NaN where
+            // it was not settled there - then a direct neighbour's value serves as the guess)
+            const float *tp = tau + sq - g.q;
+            float tprev = __ldcg(tp);
+            if (!(tprev == tprev) && ix > 0) tprev = __ldcg(tp - 1);
+            if (!(tprev == tprev) && ix + 1 < g.Wq) tprev = __ldcg(tp + 1);
+            if (!(tprev == tprev) && iy > 0) tprev = __ldcg(tp - g.Wq);
+            if (!(tprev == tprev) && iy + 1 < g.Hq) tprev = __ldcg(tp + g.Wq);
+            const float lo = kGuessLo * tprev;
+            const float hi = fminf(kGuessHi * tprev, bnd);
+            if (hi > lo) {
+                int rt = 0;                                    // smallest window holding every d < hi
+                while (rt < r && window_bound(cqy, cqx, rt, g, qy, qx) < hi) ++rt;
+                const int r0w = max(cqy - rt, 0) - wy0, r1w = min(cqy + rt, g.Hc - 1) - wy0;
+                const int c0w = max(cqx - rt, 0) - wx0, c1w = min(cqx + rt, g.Wc - 1) - wx0 + 1;
+                int below = 0;
+                for (int lr = r0w; lr <= r1w; ++lr) {
+                    const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                    for (int i = a; i < e; ++i) {
+                        const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+                        const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                                            : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                        if (d < lo) {
+                            ++below;
+                            if (FUSED) {
+                                const float2 f = s_fl[i];
+                                ay = __fadd_rn(ay, f.x);
+                                ax = __fadd_rn(ax, f.y);
+                            }
+                        } else if (d < hi) {
+                            if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = i; }
+                            ++m;
+                        }
+                    }
                 }
+                need = g.K - below;
+                resolved = need >= 1 && need <= m && m <= kListCap;
             }
-            int bstar = -1, below = 0, in_b = 0, cum = 0;
-#pragma unroll
-            for (int bk = 0; bk < 8; ++bk) {
-                const int cb = (int)(((bk < 4 ? hlo : hhi) >> ((bk & 3) << 3)) & 0xffu);
-                if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; in_b = cb; }
-                cum += cb;
-            }
-            if (bstar >= 0 && in_b <= kListCap) {
-                // ---- pass 2: accumulate sure members, collect the boundary bucket ----------------
-                int m = 0;
+        } else {
+            const int r0w = max(cqy - r, 0) - wy0, r1w = min(cqy + r, g.Hc - 1) - wy0;
+            const int c0w = max(cqx - r, 0) - wx0, c1w = min(cqx + r, g.Wc - 1) - wx0 + 1;
+            int nwin = 0;
+            for (int lr = r0w; lr <= r1w; ++lr) nwin += s_cell[lr][c1w] - s_cell[lr][c0w];
+            // density-based estimate of the K-th key and the histogram bracket around it
+            const float area = (float)((r1w - r0w + 1) * (c1w - c0w)) * g.cs * g.cs;
+            float est = (float)g.K * area / (3.14159265f * (float)max(nwin, 1));
+            if (L1D) est = sqrtf(est * 1.5707963f);        // l1 ball of radius t has area 2 t^2
+            const float lo = 0.45f * est;
+            const float hi = fminf(1.7f * est, bnd);
+            if (nwin >= g.K && nwin <= 255 && hi > lo) {
+                const float invw = 7.0f / (hi - lo);
+                // ---- pass 1: histogram ---------------------------------------------------------
+                unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit
                 for (int lr = r0w; lr <= r1w; ++lr) {
                     const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
                     for (int i = a; i < e; ++i) {
@@ -402,55 +431,77 @@ knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
                         const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
                                             : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
                         const int bk = bucket_of(d, lo, invw);
-                        if (bk < bstar) {
-                            if (FUSED) {
-                                const float2 f = s_fl[i];
-                                ay = __fadd_rn(ay, f.x);
-                                ax = __fadd_rn(ax, f.y);
+                        const unsigned inc = 1u << ((bk & 3) << 3);
+                        hlo += bk < 4 ? inc : 0u;
+                        hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                    }
+                }
+                int bstar = -1, below = 0, in_b = 0, cum = 0;
+#pragma unroll
+                for (int bk = 0; bk < 8; ++bk) {
+                    const int cb = (int)(((bk < 4 ? hlo : hhi) >> ((bk & 3) << 3)) & 0xffu);
+                    if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; in_b = cb; }
+                    cum += cb;
+                }
+                if (bstar >= 0 && in_b <= kListCap) {
+                    // ---- pass 2: accumulate sure members, collect the boundary bucket ------------
+                    for (int lr = r0w; lr <= r1w; ++lr) {
+                        const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                        for (int i = a; i < e; ++i) {
+                            const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+                            const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                                                : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                            const int bk = bucket_of(d, lo, invw);
+                            if (bk < bstar) {
+                                if (FUSED) {
+                                    const float2 f = s_fl[i];
+                                    ay = __fadd_rn(ay, f.x);
+                                    ax = __fadd_rn(ax, f.y);
+                                }
+                            } else if (bk == bstar) {
+                                s_ld[m][tid] = d;
+                                s_li[m][tid] = i;
+                                ++m;
                             }
-                        } else if (bk == bstar) {
-                            s_ld[m][tid] = d;
-                            s_li[m][tid] = i;
-                            ++m;
                         }
                     }
+                    need = g.K - below;
+                    resolved = true;
                 }
-                // order the first `need` boundary candidates by (d, trajectory index)
-                const int need = g.K - below;
-                for (int t = 0; t < need; ++t) {
-                    int best = t;
-                    float bd = s_ld[t][tid];
-                    int bj = s_pj[s_li[t][tid]];
-                    for (int u = t + 1; u < m; ++u) {
-                        const float du = s_ld[u][tid];
-                        if (du < bd || (du == bd && s_pj[s_li[u][tid]] < bj)) {
-                            best = u;
-                            bd = du;
-                            bj = s_pj[s_li[u][tid]];
-                        }
+            }
+        }
+        if (resolved) {
+            // order the first `need` boundary candidates by (d, trajectory index)
+            for (int t = 0; t < need; ++t) {
+                int best = t;
+                float bd = s_ld[t][tid];
+                int bj = s_pj[s_li[t][tid]];
+                for (int u = t + 1; u < m; ++u) {
+                    const float du = s_ld[u][tid];
+                    if (du < bd || (du == bd && s_pj[s_li[u][tid]] < bj)) {
+                        best = u;
+                        bd = du;
+                        bj = s_pj[s_li[u][tid]];
                     }
-                    const int ib = s_li[best][tid];
-                    if (best != t) {
-                        s_ld[best][tid] = s_ld[t][tid];
-                        s_li[best][tid] = s_li[t][tid];
-                        s_ld[t][tid] = bd;
-                        s_li[t][tid] = ib;
-                    }
-                    if (FUSED) {
-                        const float2 f = s_fl[ib];
-                        ay = __fadd_rn(ay, f.x);
-                        ax = __fadd_rn(ax, f.y);
-                    }
-                    t_d = bd;
-                    t_j = bj;
                 }
-                resolved = true;
+                const int ib = s_li[best][tid];
+                if (best != t) {
+                    s_ld[best][tid] = s_ld[t][tid];
+                    s_li[best][tid] = s_li[t][tid];
+                    s_ld[t][tid] = bd;
+                    s_li[t][tid] = ib;
+                }
+                if (FUSED) {
+                    const float2 f = s_fl[ib];
+                    ay = __fadd_rn(ay, f.x);
+                    ax = __fadd_rn(ax, f.y);
+                }
+                t_d = bd;
+                t_j = bj;
             }
         }
     }
 
-    const int c = iy * g.Wq + ix;
-    const int64_t sq = (int64_t)slab * g.q + c;
     if (active) {
         if (resolved) {
             tau[sq] = t_d;
@@ -463,6 +514,7 @@ knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
                 if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
             }
         } else {
+            tau[sq] = __int_as_float(0x7fc00000);              // NaN: settled later by the heap kernel
             worklist[atomicAdd(work_count, 1)] = (int)sq;
         }
     }
@@ -476,19 +528,24 @@ knn_fast_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
 // ---------------------------------------------------------------------------------------------
 // 3. work-list queries: ring search with the max-heap over the global cell list
 // ---------------------------------------------------------------------------------------------
+// bin >= 0: the work list; bin < 0: every query of every slab.
+// fused != 0 (R == 1, mean): also writes the LUT entry from the heap's members.
 __global__ void __launch_bounds__(kKnnBlock)
-knn_heap_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
-                float *__restrict__ tau, int *__restrict__ jcut, unsigned *__restrict__ tau_max,
+knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__restrict__ cell_start,
+                const float4 *__restrict__ sorted_all, float *__restrict__ tau,
+                int *__restrict__ jcut, unsigned *__restrict__ tau_max,
                 unsigned *__restrict__ tile_max, const int *__restrict__ worklist,
-                const int *__restrict__ work_count, int all_queries)
+                const int *__restrict__ work_count, int fused, float *__restrict__ lut,
+                float *__restrict__ lut_copy)
 {
     extern __shared__ float heap_mem[];
     const int tid = threadIdx.x;
-    const int64_t total = all_queries ? g.S * (int64_t)g.q : (int64_t)*work_count;
+    const int64_t total = bin < 0 ? g.S * (int64_t)g.q : (int64_t)work_count[0];
+    const int *items = worklist;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int tiles = tiles_x * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
     for (int64_t w = (int64_t)blockIdx.x * kKnnBlock + tid; w < total; w += (int64_t)gridDim.x * kKnnBlock) {
-        const int64_t sq = all_queries ? w : (int64_t)worklist[w];
+        const int64_t sq = bin < 0 ? w : (int64_t)items[w];
         const int64_t slab = sq / g.q;
         const Query q = make_query((int)(sq - slab * g.q), g);
         const int *cstart = cell_start + slab * (g.NC + 1);
@@ -520,6 +577,22 @@ knn_heap_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
         const unsigned bits = __float_as_uint(h.rootd);
         atomicMax(tau_max + slab, bits);
         atomicMax(tile_max + slab * tiles + (q.iy / kKnnTileH) * tiles_x + q.ix / kKnnTileW, bits);
+        if (fused) {
+            const int64_t b = slab / g.nb;
+            const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb)) * g.n;
+            const float2 *tmid = slab_points(traj, g, slab);
+            float ay = 0.0f, ax = 0.0f;
+            for (int k = 0; k < g.K; ++k) {
+                const int j = h.J(k);
+                const float2 pr = __ldg(tref + j), pm = __ldg(tmid + j);
+                ay = __fadd_rn(ay, __fsub_rn(pr.x, pm.x));          // focus.py:141
+                ax = __fadd_rn(ax, __fsub_rn(pr.y, pm.y));
+            }
+            const float Kf = (float)g.K;
+            const float2 v = make_float2(__fdiv_rn(ay, Kf), __fdiv_rn(ax, Kf));
+            reinterpret_cast<float2 *>(lut)[sq] = v;
+            if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
+        }
     }
 }
 
@@ -780,16 +853,29 @@ lut_backward_assemble_kernel(Geom g, const float2 *__restrict__ part, int has_ne
 // launchers
 // ---------------------------------------------------------------------------------------------
 const int *g_last_work_count = nullptr;     // inspection hook (cmax_last_worklist_count)
+int g_last_work_bins = 0;
+
+struct FastArgs {
+    const int *cell_start;
+    const float4 *sorted;
+    const float2 *sflow;
+    float *lut, *lut_copy, *tau;
+    int *jcut;
+    unsigned *tau_max, *tile_max;
+    int *worklist, *work_count;
+};
 
 template <bool L1D, bool FUSED>
-static void launch_fast(const Geom &g, dim3 grid, cudaStream_t st, const int *cell_start,
-                        const float4 *sorted, const float2 *sflow, float *lut, float *lut_copy,
-                        float *tau, int *jcut, unsigned *tau_max, unsigned *tile_max, int *worklist,
-                        int *work_count)
+static void launch_fast(const Geom &g, int bin, dim3 grid, cudaStream_t st, const FastArgs &a)
 {
-    knn_fast_kernel<L1D, FUSED><<<grid, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, lut, lut_copy,
-                                                            tau, jcut, tau_max, tile_max, worklist,
-                                                            work_count);
+    if (bin == 0)
+        knn_fast_kernel<L1D, FUSED, false><<<grid, kKnnBlock, 0, st>>>(
+            g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
+            a.tile_max, a.worklist, a.work_count);
+    else
+        knn_fast_kernel<L1D, FUSED, true><<<grid, kKnnBlock, 0, st>>>(
+            g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
+            a.tile_max, a.worklist, a.work_count);
 }
 
 int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,
@@ -805,6 +891,7 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     int *worklist = reinterpret_cast<int *>(ws + L.worklist);
     int *work_count = reinterpret_cast<int *>(ws + L.work_count);
     g_last_work_count = work_count;
+    g_last_work_bins = 1;
     float *lut = reinterpret_cast<float *>(ws + L.lut);
     const size_t smem_bin = (size_t)g.NC * sizeof(int);
     const size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
@@ -827,33 +914,38 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
         count_launch();
     }
     const int tiles = ((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
-    dim3 grid(tiles, (unsigned)g.S);
     StageScope sc(ST_KNN_SELECT, st);
     cudaMemsetAsync(tau_max, 0, sizeof(unsigned) * g.S, st);
     cudaMemsetAsync(work_count, 0, sizeof(int), st);
     // the staged fast path needs the window to fit the static tables and S*q to fit an int
     const bool can_fast = g.r_fast <= 10 && g.S * (int64_t)g.q < (int64_t)INT32_MAX;
-    const int heap_grid = 148 * 4;
+    float *lc = fused ? flow_lut_out : nullptr;
     if (can_fast) {
-        float *lc = fused ? flow_lut_out : nullptr;
-        if (g.l1dist) {
-            if (fused) launch_fast<true, true>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
-            else launch_fast<true, false>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
-        } else {
-            if (fused) launch_fast<false, true>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
-            else launch_fast<false, false>(g, grid, st, cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count);
+        const FastArgs a{cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count};
+        dim3 grid(tiles, (unsigned)g.B);
+        for (int bin = 0; bin < g.nb; ++bin) {
+            if (g.l1dist) {
+                if (fused) launch_fast<true, true>(g, bin, grid, st, a);
+                else launch_fast<true, false>(g, bin, grid, st, a);
+            } else {
+                if (fused) launch_fast<false, true>(g, bin, grid, st, a);
+                else launch_fast<false, false>(g, bin, grid, st, a);
+            }
         }
-        knn_heap_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(g, cell_start, sorted, tau, jcut, tau_max,
-                                                               tile_max, worklist, work_count, 0);
-        count_launch(2);
+        knn_heap_kernel<<<148 * 4, kKnnBlock, smem_heap, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
+                                                             tau_max, tile_max, worklist, work_count,
+                                                             fused ? 1 : 0, lut, lc);
+        count_launch(g.nb + 1);
     } else {
         cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
-        knn_heap_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(g, cell_start, sorted, tau, jcut, tau_max,
-                                                               tile_max, worklist, work_count, 1);
+        knn_heap_kernel<<<148 * 8, kKnnBlock, smem_heap, st>>>(traj, g, -1, cell_start, sorted, tau, jcut,
+                                                             tau_max, tile_max, worklist, work_count,
+                                                             fused ? 1 : 0, lut, lc);
         count_launch();
     }
+    const int acc_grid = 148 * 16;
     if (test_entry) {
-        lut_accumulate_kernel<<<heap_grid, kKnnBlock, smem_heap, st>>>(
+        lut_accumulate_kernel<<<acc_grid, kKnnBlock, smem_heap, st>>>(
             traj, g, cell_start, sorted, tau, jcut, 4, nullptr, nullptr, nullptr, nullptr, ind_out,
             dist_out, worklist, work_count, 1);
         count_launch();
@@ -862,22 +954,11 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
     float *f2n = reinterpret_cast<float *>(ws + L.f2n);
     float *wsum = reinterpret_cast<float *>(ws + L.wsum);
-    if (fused && can_fast) {
-        // LUT of the work-list queries; flow_to_next (if any) for everybody
-        lut_accumulate_kernel<<<heap_grid, kKnnBlock, 0, st>>>(
-            traj, g, cell_start, sorted, tau, jcut, 1, lut, flow_lut_out, nullptr, wsum, nullptr, nullptr,
-            worklist, work_count, 0);
-        count_launch();
-        if (want_next) {
-            lut_accumulate_kernel<<<heap_grid * 4, kKnnBlock, 0, st>>>(
-                traj, g, cell_start, sorted, tau, jcut, 2, nullptr, nullptr, f2n, wsum, nullptr, nullptr,
-                worklist, work_count, 1);
-            count_launch();
-        }
-    } else {
-        lut_accumulate_kernel<<<heap_grid * 4, kKnnBlock, 0, st>>>(
-            traj, g, cell_start, sorted, tau, jcut, 1 | (want_next ? 2 : 0), lut, flow_lut_out, f2n, wsum,
-            nullptr, nullptr, worklist, work_count, 1);
+    const int what = (fused ? 0 : 1) | (want_next ? 2 : 0);
+    if (what) {
+        lut_accumulate_kernel<<<acc_grid, kKnnBlock, 0, st>>>(
+            traj, g, cell_start, sorted, tau, jcut, what, lut, flow_lut_out, f2n, wsum, nullptr, nullptr,
+            worklist, work_count, 1);
         count_launch();
     }
     return check_launch();

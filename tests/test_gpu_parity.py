@@ -159,6 +159,39 @@ def test_knn_neighbour_sets_bit_exact(norm, shape, s, n, K):
     assert np.array_equal(dist.cpu().numpy(), dist_ref[0])
 
 
+def test_knn_temporally_coherent_slabs_bit_exact():
+    """Slabs that move smoothly (like consecutive time bins): exercises the previous-bin bracket
+    of the fast path, including cells where the bracket fails and the heap takes over."""
+    from motionpriorcmax_b200 import cabi
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    lib = cabi.load()
+    H, W, s, K, S = 96, 128, 4, 32, 8
+    rng = np.random.default_rng(42)
+    pos = fo.tile_positions((H, W), 4).astype(np.float32)
+    n = len(pos)
+    yy, xx = pos[:, 0] / H, pos[:, 1] / W
+    vel = np.stack((14 * np.sin(3.1 * xx + 1.0) * np.cos(2.3 * yy), 11 * np.cos(2.7 * yy) + 9 * xx), -1)
+    vel += rng.standard_normal(vel.shape) * 0.3
+    pts = np.stack([pos + vel * ((2 * i + 1) / (2 * S)) for i in range(S)], 0).astype(np.float32)[None]
+    pts[0, 5] += rng.standard_normal(pts[0, 5].shape).astype(np.float32) * 3.0      # a sudden jump
+    grid, Hq, Wq = fo.lut_grid((H, W), s)
+    ind_ref, dist_ref = fo.knn_bruteforce(pts, grid, K, "l2")
+    p = torch.as_tensor(pts[0], device=dev).contiguous()
+    ind = torch.empty((S, Hq * Wq, K), dtype=torch.int32, device=dev)
+    dist = torch.empty((S, Hq * Wq, K), dtype=torch.float32, device=dev)
+    need = lib.cmax_knn_workspace_bytes(H, W, s, S, n, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    rc = lib.cmax_knn_indices(cabi.ptr(p), S, n, H, W, s, K, cabi.NORM["l2"], cabi.ptr(ind),
+                              cabi.ptr(dist), cabi.ptr(ws), need, cabi.stream_ptr(dev))
+    cabi.check(rc, "cmax_knn_indices")
+    torch.cuda.synchronize()
+    assert np.array_equal(ind.cpu().numpy().astype(np.int64), ind_ref[0])
+    assert np.array_equal(dist.cpu().numpy(), dist_ref[0])
+    missed = lib.cmax_last_worklist_count(None)
+    assert 0 <= missed < 0.5 * S * Hq * Wq          # the fast path resolved most cells
+
+
 def test_zero_flow_lattice_ties():
     """All-zero flow: trajectories sit on the tile lattice, every query has 4-way ties."""
     from oracle import focus_oracle as fo
