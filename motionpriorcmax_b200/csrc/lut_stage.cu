@@ -337,21 +337,20 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     __syncthreads();
     const int total = s_rowbase[nrow];
     const bool staged = total <= kStageCap;           // CTA-uniform
-    if (staged) {
-        for (int i = tid; i < nrow * (ncol + 1); i += kKnnBlock) {
-            const int lr = i / (ncol + 1), lc = i - lr * (ncol + 1);
-            const int ga = __ldg(cstart + (wy0 + lr) * g.Wc + wx0);
-            s_cell[lr][lc] = __ldg(cstart + (wy0 + lr) * g.Wc + wx0 + lc) - ga + s_rowbase[lr];
-        }
-        for (int lr = 0; lr < nrow; ++lr) {
-            const int ga = __ldg(cstart + (wy0 + lr) * g.Wc + wx0);
+    if (staged) {                                      // one warp per window row
+        const int lane = tid & 31;
+        const float2 *sfl = FUSED ? sflow_all + (int64_t)slab * g.n : nullptr;
+        for (int lr = tid >> 5; lr < nrow; lr += kKnnBlock / 32) {
+            const int *crow = cstart + (wy0 + lr) * g.Wc + wx0;
+            const int ga = __ldg(crow);
             const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base;
-            for (int k = tid; k < len; k += kKnnBlock) {
+            for (int lc = lane; lc <= ncol; lc += 32) s_cell[lr][lc] = __ldg(crow + lc) - ga + base;
+            for (int k = lane; k < len; k += 32) {
                 const float4 rec = __ldg(sorted + ga + k);
                 s_py[base + k] = rec.x;
                 s_px[base + k] = rec.y;
                 s_pj[base + k] = __float_as_int(rec.z);
-                if (FUSED) s_fl[base + k] = __ldg(sflow_all + (int64_t)slab * g.n + ga + k);
+                if (FUSED) s_fl[base + k] = __ldg(sfl + ga + k);
             }
         }
     }
@@ -387,6 +386,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 const int r0w = max(cqy - rt, 0) - wy0, r1w = min(cqy + rt, g.Hc - 1) - wy0;
                 const int c0w = max(cqx - rt, 0) - wx0, c1w = min(cqx + rt, g.Wc - 1) - wx0 + 1;
                 int below = 0;
+                const float invw = 7.0f / (hi - lo);
+                unsigned hlo = 0u, hhi = 0u;                   // 7 bracket slices x 8-bit counters
                 for (int lr = r0w; lr <= r1w; ++lr) {
                     const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
                     for (int i = a; i < e; ++i) {
@@ -401,13 +402,46 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                                 ax = __fadd_rn(ax, f.y);
                             }
                         } else if (d < hi) {
-                            if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = i; }
+                            const int bk = bucket_of(d, lo, invw);     // 1..8
+                            const unsigned inc = 1u << ((bk & 3) << 3);
+                            hlo += bk < 4 ? inc : 0u;
+                            hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                            if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = (bk << 16) | i; }
                             ++m;
                         }
                     }
                 }
-                need = g.K - below;
-                resolved = need >= 1 && need <= m && m <= kListCap;
+                // slice of the bracket that holds the K-th key
+                int bstar = -1, cum = below;
+#pragma unroll
+                for (int bk = 1; bk < 8; ++bk) {
+                    const int cb = (int)(((bk < 4 ? hlo : hhi) >> ((bk & 3) << 3)) & 0xffu);
+                    if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; }
+                    cum += cb;
+                }
+                if (below < g.K && bstar > 0 && m <= kListCap) {
+                    // members of the lower slices are accumulated, the slice itself is compacted
+                    int mm = 0;
+                    for (int u = 0; u < m; ++u) {
+                        const int pk = s_li[u][tid];
+                        const int bk = pk >> 16, i = pk & 0xffff;
+                        if (bk < bstar) {
+                            if (FUSED) {
+                                const float2 f = s_fl[i];
+                                ay = __fadd_rn(ay, f.x);
+                                ax = __fadd_rn(ax, f.y);
+                            }
+                        } else if (bk == bstar) {
+                            const float d = s_ld[u][tid];
+                            s_ld[mm][tid] = d;
+                            s_li[mm][tid] = i;
+                            ++mm;
+                        }
+                    }
+                    m = mm;
+                    need = g.K - below;
+                    resolved = true;
+                }
             }
         } else {
             const int r0w = max(cqy - r, 0) - wy0, r1w = min(cqy + r, g.Hc - 1) - wy0;
