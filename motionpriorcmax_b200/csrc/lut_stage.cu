@@ -388,28 +388,45 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 int below = 0;
                 const float invw = 7.0f / (hi - lo);
                 unsigned hlo = 0u, hhi = 0u;                   // 7 bracket slices x 8-bit counters
+                auto visit = [&](float d, int i) {
+                    if (d < lo) {
+                        ++below;
+                        if (FUSED) {
+                            const float2 f = s_fl[i];
+                            ay = __fadd_rn(ay, f.x);
+                            ax = __fadd_rn(ax, f.y);
+                        }
+                    } else if (d < hi) {
+                        if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = i; }
+                        ++m;
+                    }
+                };
+                auto dist_at = [&](int i) {
+                    const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+                    return L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                               : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                };
                 for (int lr = r0w; lr <= r1w; ++lr) {
                     const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
-                    for (int i = a; i < e; ++i) {
-                        const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
-                        const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
-                                            : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
-                        if (d < lo) {
-                            ++below;
-                            if (FUSED) {
-                                const float2 f = s_fl[i];
-                                ay = __fadd_rn(ay, f.x);
-                                ax = __fadd_rn(ax, f.y);
-                            }
-                        } else if (d < hi) {
-                            const int bk = bucket_of(d, lo, invw);     // 1..8
-                            const unsigned inc = 1u << ((bk & 3) << 3);
-                            hlo += bk < 4 ? inc : 0u;
-                            hhi += (bk >= 4 && bk < 8) ? inc : 0u;
-                            if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = (bk << 16) | i; }
-                            ++m;
-                        }
+                    int i = a;
+                    for (; i + 4 <= e; i += 4) {          // distances first (4 loads in flight)
+                        const float d0 = dist_at(i), d1 = dist_at(i + 1), d2 = dist_at(i + 2),
+                                    d3 = dist_at(i + 3);
+                        visit(d0, i);
+                        visit(d1, i + 1);
+                        visit(d2, i + 2);
+                        visit(d3, i + 3);
                     }
+                    for (; i < e; ++i) visit(dist_at(i), i);
+                }
+                // slice the listed candidates (kept out of the hot loop: nearly every warp
+                // iteration has *some* lane inside the bracket)
+                for (int u = 0; u < min(m, kListCap); ++u) {
+                    const int bk = bucket_of(s_ld[u][tid], lo, invw);     // 1..8
+                    const unsigned inc = 1u << ((bk & 3) << 3);
+                    hlo += bk < 4 ? inc : 0u;
+                    hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                    s_li[u][tid] |= bk << 16;
                 }
                 // slice of the bracket that holds the K-th key
                 int bstar = -1, cum = below;
