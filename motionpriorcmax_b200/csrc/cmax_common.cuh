@@ -112,6 +112,13 @@ __device__ __forceinline__ float2 ld_stream_f2(const float *p)
     return r;
 }
 
+// Two adjacent floats in one L2 atomic request (sm_90+): halves the red traffic of (gy, gx)
+// pairs and of x-adjacent bilinear corners.  `p` must be 8-byte aligned.
+__device__ __forceinline__ void red_add_f32x2(float *p, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 // Python-style float floor division, the arithmetic of torch's `//` on float tensors
 // (c10 div_floor_floating) used by focus.py:186-187.
 __device__ __forceinline__ float floordiv_f32(float a, float b)

@@ -80,14 +80,25 @@ event_forward_kernel(const float *__restrict__ events, const float *__restrict__
         v[2] = __fmul_rn(__fmul_rn(oy, c.fx), w);
         v[3] = __fmul_rn(__fmul_rn(c.fy, c.fx), w);
         const int64_t base = ((b * g.R + r) * g.P + pol) * HW;
+        if (DET) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (c.idx[k] >= 0) {
-                if (DET)
+            for (int k = 0; k < 4; ++k)
+                if (c.idx[k] >= 0)
                     atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + c.idx[k]),
                               (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
-                else
-                    atomicAdd(raw + base + c.idx[k], v[k]);
+        } else {
+            // corners (y, x1) and (y, x1+1) are adjacent floats: one vector red when 8 B aligned
+            // (plane base and row pitch are even, so alignment depends on x1 only)
+#pragma unroll
+            for (int row = 0; row < 2; ++row) {
+                const int i0 = c.idx[row], i1 = c.idx[row + 2];
+                float *p0 = raw + base + i0;
+                if (i0 >= 0 && i1 >= 0 && (((base + i0) & 1) == 0)) {
+                    red_add_f32x2(p0, v[row], v[row + 2]);
+                } else {
+                    if (i0 >= 0) atomicAdd(p0, v[row]);
+                    if (i1 >= 0) atomicAdd(raw + base + i1, v[row + 2]);
+                }
             }
         }
     }
@@ -144,9 +155,7 @@ event_backward_kernel(const float *__restrict__ events, const float *__restrict_
             atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
             atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
         } else {
-            float *dst = dlut + (cell * g.R + r) * 2;
-            atomicAdd(dst, coef * gy);
-            atomicAdd(dst + 1, coef * gx);
+            red_add_f32x2(dlut + (cell * g.R + r) * 2, coef * gy, coef * gx);
         }
     }
 }
