@@ -820,15 +820,18 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
         const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
         const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
         const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
-        const int nx = ix1 - ix0 + 1;
-        const float qx0 = __fadd_rn((float)(ix0 * g.s), g.off);
-        for (int iy = iy0; iy <= iy1 && nx > 0; ++iy) {
+        for (int iy = iy0; iy <= iy1 && ix0 <= ix1; ++iy) {
             const float qy = __fadd_rn((float)(iy * g.s), g.off);
             const float dy = __fsub_rn(qy, p.x);
             const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
-            const int o = iy * Wq + ix0;
+            // clip the row to the reach disc (l1: diamond); conservative by one cell
+            const float hx = L1D ? rho - fabsf(dy) : sqrtf(fmaxf(rho * rho - dy * dy, 0.0f));
+            const int jx0 = max(ix0, (int)floorf((p.y - hx - g.off) * inv_s));
+            const int jx1 = min(ix1, (int)ceilf((p.y + hx - g.off) * inv_s));
+            const int nx = jx1 - jx0 + 1;
+            const int o = iy * Wq + jx0;
             const float *tp = tau_s + o;
-            float qx = qx0;                       // exact: lattice coordinates are multiples of 0.5
+            float qx = __fadd_rn((float)(jx0 * g.s), g.off);   // exact: multiples of 0.5
 #pragma unroll 4
             for (int k = 0; k < nx; ++k, qx += fs) {
                 const float dx = __fsub_rn(qx, p.y);

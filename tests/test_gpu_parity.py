@@ -396,3 +396,20 @@ def test_front_end_matches_oracle_and_golden():
         ref = fo.trajectories_backward(gout.cpu().numpy(), c["times"], patch, K, basis,
                                        c["coeff_grid"].shape)
         assert rel_err(cg.grad.cpu().numpy(), ref) < 1e-5
+
+
+def test_event_uploader_recreates_the_padded_batch():
+    from motionpriorcmax_b200 import synthetic
+    from motionpriorcmax_b200.io import EventUploader
+    dev = _cuda()
+    up = EventUploader(dev)
+    for counts in ([900, 300, 40], [100, 800, 0], [500, 500, 500]):
+        ev, npos = synthetic.make_event_batch(3, counts, 48, 64, 15, True, seed=sum(counts))
+        if ev.shape[1] != 1200:                      # same padded length so buffers are reused
+            ev = torch.cat((ev, torch.zeros(3, 1200 - ev.shape[1], 6)), 1)
+        buf, slot = up.upload(ev.pin_memory(), npos)
+        up.wait(slot)
+        torch.cuda.synchronize()
+        assert torch.equal(buf.cpu(), ev)
+        assert up.bytes_last == int(ev[..., 5].sum().item()) * 24
+        up.release(slot)

@@ -99,3 +99,14 @@ def test_tile_mask_and_basis_table_match_oracle():
         got = tj.basis_table(times, K, basis).numpy()
         want = fo.basis_matrix(times.numpy(), K, basis) - fo.basis_matrix([0.0], K, basis)
         assert np.allclose(got, want, rtol=2e-6, atol=1e-7), basis
+
+
+def test_valid_prefix_lengths_match_the_valid_column():
+    from motionpriorcmax_b200 import synthetic
+    from motionpriorcmax_b200.io import valid_prefix_lengths
+    ev, npos = synthetic.make_event_batch(4, [5000, 9000, 100, 0], 48, 64, 15, True, seed=2)
+    got = valid_prefix_lengths(ev, npos)
+    want = np.stack([[int((ev[b, :npos, 5] > 0).sum()), int((ev[b, npos:, 5] > 0).sum())] for b in range(4)])
+    assert np.array_equal(got, want)
+    ev2, _ = synthetic.make_event_batch(3, [50, 0, 7], 48, 64, 15, False, seed=2)
+    assert valid_prefix_lengths(ev2, None)[:, 0].tolist() == [50, 0, 7]
