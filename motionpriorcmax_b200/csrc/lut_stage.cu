@@ -302,7 +302,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     __shared__ unsigned blk_max;
 
     const int tid = threadIdx.x;
-    const int slab = blockIdx.y * g.nb + bin;
+    const int slab = bin < 0 ? blockIdx.y : blockIdx.y * g.nb + bin;     // bin < 0: all slabs
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
@@ -922,7 +922,7 @@ struct FastArgs {
 template <bool L1D, bool FUSED>
 static void launch_fast(const Geom &g, int bin, dim3 grid, cudaStream_t st, const FastArgs &a)
 {
-    if (bin == 0)
+    if (bin <= 0)
         knn_fast_kernel<L1D, FUSED, false><<<grid, kKnnBlock, 0, st>>>(
             g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
             a.tile_max, a.worklist, a.work_count);
@@ -976,8 +976,11 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     float *lc = fused ? flow_lut_out : nullptr;
     if (can_fast) {
         const FastArgs a{cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count};
-        dim3 grid(tiles, (unsigned)g.B);
-        for (int bin = 0; bin < g.nb; ++bin) {
+        // Few samples: per-bin launches (previous-bin bracket) would serialise 15 tiny grids, so
+        // run the self-contained two-pass kernel on every slab at once instead.
+        const bool per_bin = g.B >= 6;
+        dim3 grid(tiles, (unsigned)(per_bin ? g.B : g.S));
+        for (int bin = per_bin ? 0 : -1; bin < (per_bin ? g.nb : 0); ++bin) {
             if (g.l1dist) {
                 if (fused) launch_fast<true, true>(g, bin, grid, st, a);
                 else launch_fast<true, false>(g, bin, grid, st, a);
@@ -989,7 +992,7 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
         knn_heap_kernel<<<148 * 4, kKnnBlock, smem_heap, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
                                                              tau_max, tile_max, worklist, work_count,
                                                              fused ? 1 : 0, lut, lc);
-        count_launch(g.nb + 1);
+        count_launch((per_bin ? g.nb : 1) + 1);
     } else {
         cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
         knn_heap_kernel<<<148 * 8, kKnnBlock, smem_heap, st>>>(traj, g, -1, cell_start, sorted, tau, jcut,
