@@ -7,7 +7,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_referen
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --prof-warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_launch.log 2>&1
 tail -1 gpurun_out/ncu_launch.log | cut -c1-300
-ncu --set full --clock-control none --import-source on -k regex:"bin_points|knn_|lut_|event_|image_|smooth_|finalize|traj_" -s 14 -c 14 \
+ncu --set full --clock-control none --import-source on -k regex:"bin_points|knn_|lut_|event_|image_|smooth_|finalize|traj_" -s 28 -c 28 \
     -o gpurun_out/prof_full -f python bench.py --steps 1 --prof-warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
 tail -1 gpurun_out/ncu_full.log
 ls -la gpurun_out | head -20

@@ -1,0 +1,80 @@
+"""Event-count sweep (BASELINE.json configs[4]): loss fwd+bwd events/s vs events per window.
+Windows are generated on the device (uniform events, time sorted, loader layout).
+    python scripts/sweep.py [--batch 1,14] [--events 1e5,...] > profiles/rXX_sweep.json
+"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from motionpriorcmax_b200 import synthetic, trajectories as tj, cabi
+from motionpriorcmax_b200.losses import LossFactory
+
+
+def device_batch(B, M, H, W, nb, dev, seed):
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    npos = M // 2
+    ev = torch.empty(B, M, 6, device=dev)
+    for b in range(B):
+        for s, e, pol in ((0, npos, 1.0), (npos, M, 0.0)):
+            n = e - s
+            t = torch.rand(n, device=dev, generator=g).sort().values
+            t = (t - t[0]) / (t[-1] - t[0])
+            ev[b, s:e, 0] = torch.rand(n, device=dev, generator=g) * (H - 1e-3)
+            ev[b, s:e, 1] = torch.rand(n, device=dev, generator=g) * (W - 1e-3)
+            ev[b, s:e, 2] = t
+            ev[b, s:e, 3] = pol
+            ev[b, s:e, 4] = torch.clamp((t * nb).floor(), max=nb - 1)
+            ev[b, s:e, 5] = 1.0
+    return ev, npos
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", default="1,14")
+    ap.add_argument("--events", default="1e5,3e5,1e6,3e6,1e7,3e7,5e7")
+    ap.add_argument("--steps", type=int, default=10)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+    H, W = cfg["image_shape"]
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg))
+    times = L.get_reconstruction_times(dev); times[0] = 0.5
+    peak = 6553.6
+    try:
+        peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+    except Exception:
+        pass
+    rows = []
+    for B in [int(x) for x in a.batch.split(",")]:
+        cg = synthetic.make_coeff_grid(B, 1, H, W, sigma_px=8.0, seed=1234).to(dev).requires_grad_()
+        for M in [int(float(x)) for x in a.events.split(",")]:
+            if B * M * 24 > 40e9:
+                continue
+            ev, npos = device_batch(B, M, H, W, cfg["num_bins"], dev, seed=B * 1000 + 7)
+
+            def step():
+                cg.grad = None
+                traj = tj.calculate_trajectories_at_t(cg, times, 4, 1, "polynomial")
+                loss, _, _ = L.calc(traj, times, {"events": ev, "num_pos_events": npos})
+                loss.backward()
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                step()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            n_t, n, Q = 16, 19200, 15 * 19200
+            bytes_alg = 48 * B * M + 20 * B * 2 * H * W + 24 * B * Q + 16 * B * n_t * n
+            rows.append({"B": B, "events_per_window": M, "ms_per_step": ms, "events_per_s": B * M / ms * 1e3,
+                         "algorithmic_GB": bytes_alg / 1e9, "achieved_GBps": bytes_alg / ms / 1e6,
+                         "hbm_frac": bytes_alg / ms / 1e6 / peak})
+            print(json.dumps(rows[-1]), file=sys.stderr)
+            del ev
+            torch.cuda.empty_cache()
+    print(json.dumps({"peak_GBps": peak, "rows": rows}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
