@@ -378,8 +378,9 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
             if (!(tprev == tprev) && ix + 1 < g.Wq) tprev = __ldcg(tp + 1);
             if (!(tprev == tprev) && iy > 0) tprev = __ldcg(tp - g.Wq);
             if (!(tprev == tprev) && iy + 1 < g.Hq) tprev = __ldcg(tp + g.Wq);
-            const float lo = kGuessLo * tprev;
-            const float hi = fminf(kGuessHi * tprev, bnd);
+            const float pred = tprev;
+            const float lo = kGuessLo * pred;
+            const float hi = fminf(kGuessHi * pred, bnd);
             if (hi > lo) {
                 int rt = 0;                                    // smallest window holding every d < hi
                 while (rt < r && window_bound(cqy, cqx, rt, g, qy, qx) < hi) ++rt;
