@@ -619,9 +619,34 @@ knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__re
             ++r;
             scan_cells(cstart, sorted, q.cqy - r, q.cqx - r, q.cqx + r, g, q.qy, q.qx, ins);
             scan_cells(cstart, sorted, q.cqy + r, q.cqx - r, q.cqx + r, g, q.qy, q.qx, ins);
-            for (int row = q.cqy - r + 1; row <= q.cqy + r - 1; ++row) {
-                scan_cells(cstart, sorted, row, q.cqx - r, q.cqx - r, g, q.qy, q.qx, ins);
-                scan_cells(cstart, sorted, row, q.cqx + r, q.cqx + r, g, q.qy, q.qx, ins);
+            // left / right columns of the ring: fetch the run extents of four rows at once (16
+            // independent loads in flight) before touching the heap - the ring walk is otherwise
+            // one long chain of dependent look-ups
+            const int cl = q.cqx - r, cr = q.cqx + r;
+            const bool okl = cl >= 0, okr = cr < g.Wc;
+            for (int row0 = max(q.cqy - r + 1, 0); row0 <= min(q.cqy + r - 1, g.Hc - 1); row0 += 4) {
+                int aL[4], eL[4], aR[4], eR[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = row0 + u;
+                    const bool ok = row <= min(q.cqy + r - 1, g.Hc - 1);
+                    const int *cp = cstart + row * g.Wc;
+                    aL[u] = ok && okl ? __ldg(cp + cl) : 0;
+                    eL[u] = ok && okl ? __ldg(cp + cl + 1) : 0;
+                    aR[u] = ok && okr ? __ldg(cp + cr) : 0;
+                    eR[u] = ok && okr ? __ldg(cp + cr + 1) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    for (int i = aL[u]; i < eL[u]; ++i) {
+                        const float4 rec = __ldg(sorted + i);
+                        ins(knn_dist(q.qy, q.qx, rec.x, rec.y, g.l1dist), rec);
+                    }
+                    for (int i = aR[u]; i < eR[u]; ++i) {
+                        const float4 rec = __ldg(sorted + i);
+                        ins(knn_dist(q.qy, q.qx, rec.x, rec.y, g.l1dist), rec);
+                    }
+                }
             }
         }
         tau[sq] = h.rootd;
