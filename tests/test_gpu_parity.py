@@ -421,3 +421,39 @@ def test_event_uploader_recreates_the_padded_batch():
         assert torch.equal(buf.cpu(), ev)
         assert up.bytes_last == int(ev[..., 5].sum().item()) * 24
         up.release(slot)
+
+
+def test_many_free_trajectories_large_n():
+    """The image-logging callback passes GT-flow trajectories masked by flow_valid: n is not the
+    tile lattice and can exceed 65 535.  Dense, unstructured point sets leave the
+    staged fast path for the heap search - results must still match exhaustive search."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(120, 160), num_bins=3, num_knn=32)
+    H, W = cfg["image_shape"]
+    rng = np.random.default_rng(5)
+    n = 70_000
+    times = fo.reconstruction_times(1, 3, 0.6)
+    p0 = (rng.random((1, 1, n, 2)) * [H, W]).astype(np.float32)
+    vel = (rng.standard_normal((1, 1, n, 2)) * 2).astype(np.float32)
+    traj = (p0 + vel * times[None, :, None, None]).astype(np.float32)
+    ev, npos = synthetic.make_event_batch(1, 20000, H, W, 3, True, seed=4)
+    r = _run_loss(cfg, traj, times, ev.numpy(), npos)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev.numpy(), npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["lut"], f["flow_lut"]) < TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev.numpy(), npos)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ddp_example_two_gpus():
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "examples", "ddp_flow_training_step.py"), "--steps", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "step 1: loss=" in out.stdout
