@@ -457,3 +457,78 @@ def test_ddp_example_two_gpus():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "step 1: loss=" in out.stdout
+
+
+def test_full_size_evimo2_bezier_window_matches_oracle():
+    """BASELINE.json configs[2]: EVIMO2 shape 384x512, 41 bins, Bezier degree 10 (x-major
+    parameters), smoothness on flow_to_next, as in the experiment yaml."""
+    from motionpriorcmax_b200 import synthetic, trajectories as tj
+    from motionpriorcmax_b200.losses import LossFactory
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    cfg = dict(synthetic.EVIMO2_LOSS_CONFIG)
+    H, W = cfg["image_shape"]
+    deg = 10
+    times = fo.reconstruction_times(1, cfg["num_bins"], 0.35)
+    cg = synthetic.make_coeff_grid(1, deg, H, W, sigma_px=5.0, seed=21, coarse=(6, 8))   # [1,1,20,H,W]
+    ev, npos = synthetic.make_event_batch(1, 150_000, H, W, cfg["num_bins"], True, seed=21,
+                                          integer_coords=True, coord_scale=0.8)
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg))
+    cgd = cg.to(dev).requires_grad_()
+    traj = tj.calculate_trajectories_at_t(cgd, torch.as_tensor(times, device=dev), 4, deg, "bezier",
+                                          xy_order=True)
+    loss, log, misc = L.calc(traj, torch.as_tensor(times, device=dev),
+                             {"events": ev.to(dev), "num_pos_events": npos}, return_flow_lut=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    tr_ref, _ = fo.trajectories_from_coeff_grid(cg.numpy(), times, 4, deg, "bezier", xy_order=True)
+    assert rel_err(traj.detach().cpu().numpy(), tr_ref) < 1e-6
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(tr_ref, times, ev.numpy(), npos)
+    g = o.backward()
+    dcg = fo.trajectories_backward(g["dtraj"], times, 4, deg, "bezier", tuple(cg.shape), xy_order=True)
+    assert abs(loss.item() - f["loss"]) <= TOL * abs(f["loss"])
+    assert abs(log["smoothness_loss"].item() - f["smoothness_loss"]) <= TOL * abs(f["smoothness_loss"])
+    assert rel_err(misc["flow_lut"].cpu().numpy(), f["flow_lut"]) < TOL
+    assert rel_err(misc["iwes"].cpu().numpy(), f["iwes"]) < TOL
+    e = rel_err(cgd.grad.cpu().numpy(), dcg)
+    assert e < 5e-3 if cfg["focus_loss_norm"] == "l1" else e < 2 * TOL, e
+    scale = np.abs(dcg).max()
+    assert (np.abs(cgd.grad.cpu().numpy() - dcg) > 1e-4 * scale).mean() < 2e-3
+
+
+def test_k3_polynomial_deterministic_mode_full_size():
+    """BASELINE.json configs[3]: DSEC shape, polynomial K=3, deterministic int64 accumulation:
+    two runs bit-identical, float results within 1e-5 of the float64 oracle."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 1, 400_000, 3, seed=33)
+    a = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    b = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    assert a["loss"] == b["loss"]
+    for k in ("iwes", "lut", "dtraj"):
+        assert np.array_equal(a[k], b[k]), k
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(a["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(a["iwes"], f["iwes"]) < TOL and rel_err(a["lut"], f["flow_lut"]) < TOL
+    _assert_grad_close(a["dtraj"], g["dtraj"], cfg, traj, times, ev, npos)
+
+
+def test_ten_reference_times():
+    """The "10 reference times" variant of configs[2]: n_tref=10, pab off, scale off."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = synthetic.multi_tref_variant(dict(synthetic.EVIMO2_LOSS_CONFIG, image_shape=(96, 128), num_bins=11,
+                                            num_knn=16, focus_loss_norm="l2"), 10)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 15000, 2, seed=8)
+    r = _run_loss(cfg, traj, times, ev, npos)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert r["iwes"].shape == (2, 10, 96, 128)
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["iwes"], f["iwes"]) < TOL and rel_err(r["lut"], f["flow_lut"]) < TOL
+    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
