@@ -532,3 +532,21 @@ def test_ten_reference_times():
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(r["iwes"], f["iwes"]) < TOL and rel_err(r["lut"], f["flow_lut"]) < TOL
     assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+
+
+@pytest.mark.timeout(120)
+def test_non_finite_trajectories_do_not_hang():
+    """Diverged training can hand NaN / Inf trajectories to the loss; the kernels must terminate
+    (the reference would produce NaN too) and leave the device usable."""
+    from motionpriorcmax_b200 import synthetic
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(64, 96), num_knn=8, num_bins=4)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 5000, 1, seed=3)
+    bad = traj.copy()
+    bad[0, :, ::7] = np.nan
+    bad[1, 2, ::5] = np.inf
+    r = _run_loss(cfg, bad, times, ev, npos)
+    assert r["iwes"].shape == (2, 1, 2, 64, 96)
+    all_nan = np.full_like(traj, np.nan)
+    _run_loss(cfg, all_nan, times, ev, npos)
+    ok = _run_loss(cfg, traj, times, ev, npos)          # device still healthy afterwards
+    assert np.isfinite(ok["loss"]) and np.isfinite(ok["dtraj"]).all()
