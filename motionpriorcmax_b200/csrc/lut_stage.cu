@@ -301,6 +301,9 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     __shared__ int s_rowbase[kWinRows + 1];
     __shared__ unsigned blk_max;
 
+    // Programmatic dependent launch: the next bin's grid may start (and stage its window) while
+    // this grid drains; it waits (griddepcontrol.wait) before it reads this grid's tau.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x;
     const int slab = bin < 0 ? blockIdx.y : blockIdx.y * g.nb + bin;     // bin < 0: all slabs
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
@@ -356,6 +359,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     }
     __syncthreads();
 
+    if (GUESS) asm volatile("griddepcontrol.wait;" ::: "memory");     // previous bin's tau is final
     const int c = iy * g.Wq + ix;
     const int64_t sq = (int64_t)slab * g.q + c;
     bool resolved = false;
@@ -952,10 +956,21 @@ static void launch_fast(const Geom &g, int bin, dim3 grid, cudaStream_t st, cons
         knn_fast_kernel<L1D, FUSED, false><<<grid, kKnnBlock, 0, st>>>(
             g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
             a.tile_max, a.worklist, a.work_count);
-    else
-        knn_fast_kernel<L1D, FUSED, true><<<grid, kKnnBlock, 0, st>>>(
-            g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
-            a.tile_max, a.worklist, a.work_count);
+    else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kKnnBlock);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, knn_fast_kernel<L1D, FUSED, true>, g, bin, a.cell_start, a.sorted, a.sflow,
+                           a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max, a.tile_max, a.worklist,
+                           a.work_count);
+    }
 }
 
 int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,
