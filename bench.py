@@ -2,7 +2,7 @@
 """bench.py - CMax loss forward+backward throughput (events/s) on B200, per BASELINE.json.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--events M] [--batch B] [--variant dsec|dsec_tref5|evimo2|k3_det] [--sweep]
+                    [--events M] [--batch B] [--variant dsec|dsec_tref5|evimo2|k3_det]
 
 One "step" = one pass of the loss hot path over one batch of synthetic event windows:
 coeff_grid -> trajectories (fused front end) -> FocusLoss.calc -> backward to d coeff_grid.
@@ -82,7 +82,7 @@ def make_inputs(cfg, w, rank: int):
     return cg, ev, npos, n_valid
 
 
-def algorithmic_bytes(cfg, w, B, M, n, include_knn_idx=False):
+def algorithmic_bytes(cfg, w, B, M, n):
     """bytes_alg = 48 E + 20 B R P H W + 24 B Q R + 16 B n_t n."""
     H, W = cfg["image_shape"]
     R, nb, s = cfg["num_tref"], cfg["num_bins"], cfg["lut_superpixel_size"]

@@ -47,7 +47,6 @@ struct Header {               // first 1 KiB of the workspace
     double smooth_sum;        // sum of charbonnier terms (x and y)
     float val;                // focus_sum / N
     float focus, smooth, loss;
-    int n_focus_partials, n_smooth_partials;
 };
 
 struct Layout {

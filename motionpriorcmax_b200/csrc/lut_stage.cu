@@ -687,14 +687,12 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
                       const int *__restrict__ jcut, int what, float *__restrict__ lut,
                       float *__restrict__ lut_copy, float *__restrict__ f2n,
                       float *__restrict__ wsum, int32_t *__restrict__ ind_out,
-                      float *__restrict__ dist_out, const int *__restrict__ worklist,
-                      const int *__restrict__ work_count, int all_queries)
+                      float *__restrict__ dist_out)
 {
     extern __shared__ float heap_mem[];
     const int tid = threadIdx.x;
-    const int64_t total = all_queries ? g.S * (int64_t)g.q : (int64_t)*work_count;
-    for (int64_t w = (int64_t)blockIdx.x * kKnnBlock + tid; w < total; w += (int64_t)gridDim.x * kKnnBlock) {
-        const int64_t sq = all_queries ? w : (int64_t)worklist[w];
+    const int64_t total = g.S * (int64_t)g.q;
+    for (int64_t sq = (int64_t)blockIdx.x * kKnnBlock + tid; sq < total; sq += (int64_t)gridDim.x * kKnnBlock) {
         const int64_t slab = sq / g.q;
         const int c = (int)(sq - slab * g.q);
         const Query q = make_query(c, g);
@@ -1045,7 +1043,7 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     if (test_entry) {
         lut_accumulate_kernel<<<acc_grid, kKnnBlock, smem_heap, st>>>(
             traj, g, cell_start, sorted, tau, jcut, 4, nullptr, nullptr, nullptr, nullptr, ind_out,
-            dist_out, worklist, work_count, 1);
+            dist_out);
         count_launch();
         return check_launch();
     }
@@ -1055,8 +1053,7 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     const int what = (fused ? 0 : 1) | (want_next ? 2 : 0);
     if (what) {
         lut_accumulate_kernel<<<acc_grid, kKnnBlock, 0, st>>>(
-            traj, g, cell_start, sorted, tau, jcut, what, lut, flow_lut_out, f2n, wsum, nullptr, nullptr,
-            worklist, work_count, 1);
+            traj, g, cell_start, sorted, tau, jcut, what, lut, flow_lut_out, f2n, wsum, nullptr, nullptr);
         count_launch();
     }
     return check_launch();

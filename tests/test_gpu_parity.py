@@ -550,3 +550,13 @@ def test_non_finite_trajectories_do_not_hang():
     _run_loss(cfg, all_nan, times, ev, npos)
     ok = _run_loss(cfg, traj, times, ev, npos)          # device still healthy afterwards
     assert np.isfinite(ok["loss"]) and np.isfinite(ok["dtraj"]).all()
+
+
+def test_zero_length_event_tensor():
+    """M = 0: no event kernel is launched; the IWE is empty, 1/mean(0) = inf like the reference."""
+    from motionpriorcmax_b200 import synthetic
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(32, 48), num_knn=4, num_bins=3)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 10, 1, seed=9)
+    r = _run_loss(cfg, traj, times, ev[:, :0], 0)
+    assert np.isinf(r["loss"]) and np.abs(r["iwes"]).max() == 0.0
+    assert r["lut"].shape == (2, 3, 8, 12, 1, 2) and np.isfinite(r["lut"]).all()
