@@ -988,7 +988,10 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     float *lut = reinterpret_cast<float *>(ws + L.lut);
     const size_t smem_bin = (size_t)g.NC * sizeof(int);
     const size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // opt-in shared-memory sizes are per device
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool &attr_done = attr_done_dev[dev_id & 63];
     if (!attr_done) {
         cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kMaxCells * (int)sizeof(int));
