@@ -134,6 +134,14 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
                                int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
                                int32_t xy_order, float *dcoeff_grid_out, void *stream);
 
+/* Event voxel grid (the network input), upstream VoxelGrid.convert (src/loader/dsec/utils.py:29-77):
+ * trilinear vote of 2p-1 into grid_out [C, H, W] with t_norm = (C-1)(t - t[0])/(t[n-1] - t[0]),
+ * then norm_type 0: none, 1: 'mean_std' over the non-zero entries (unbiased std), 2: 'max'.
+ *   x, y, t, p [n] float32 (t sorted);  stats_scratch: 4 doubles (required when norm_type != 0). */
+int cmax_voxel_grid(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                    int32_t C, int32_t H, int32_t W, int32_t norm_type, float *grid_out,
+                    double *stats_scratch, void *stream);
+
 /* Micro-benchmark used by bench.py to measure the atomic side of the roofline on the box:
  * n_ops float32 `red.global.add` to pseudo-random addresses inside `region_floats` floats.
  * mode 0: global red.f32, 1: shared-memory atomics + flush, 2: global red on int64. */

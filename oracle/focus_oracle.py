@@ -369,6 +369,33 @@ def create_iwe(events, image_shape, weight=1.0, sigma=1, dtype=np.float32) -> np
     return blur(img, sigma) if sigma > 0 else img
 
 
+def voxel_grid(x, y, t, p, shape, norm_type=None):
+    """src/loader/dsec/utils.py:29-77 (VoxelGrid.convert, quantile == 0): trilinear vote of 2p-1,
+    int() truncation toward zero, float32 arithmetic, then 'mean_std' / 'max' normalisation."""
+    C, H, W = shape
+    x, y, t, p = (np.asarray(v, np.float32) for v in (x, y, t, p))
+    tn = (np.float32(C - 1) * (t - t[0]) / (t[-1] - t[0])).astype(np.float32)
+    x0, y0, t0 = np.trunc(x).astype(np.int64), np.trunc(y).astype(np.int64), np.trunc(tn).astype(np.int64)
+    value = np.float32(2) * p - np.float32(1)
+    grid = np.zeros(C * H * W, np.float64)
+    for xl in (x0, x0 + 1):
+        for yl in (y0, y0 + 1):
+            for tl in (t0, t0 + 1):
+                m = (xl < W) & (xl >= 0) & (yl < H) & (yl >= 0) & (tl >= 0) & (tl < C)
+                w = value * (1 - np.abs(xl.astype(np.float32) - x)) * (1 - np.abs(yl.astype(np.float32) - y)) \
+                    * (1 - np.abs(tl.astype(np.float32) - tn))
+                np.add.at(grid, (H * W * tl + W * yl + xl)[m], w[m].astype(np.float64))
+    grid = grid.astype(np.float32).reshape(C, H, W)
+    nz = grid != 0
+    if norm_type == "mean_std" and nz.any():
+        mean = grid[nz].mean(dtype=np.float64)
+        std = grid[nz].std(ddof=1, dtype=np.float64) if nz.sum() > 1 else np.nan
+        grid[nz] = (grid[nz] - np.float32(mean)) / np.float32(std) if std > 0 else grid[nz] - np.float32(mean)
+    elif norm_type == "max" and np.abs(grid).max() > 0:
+        grid = grid / np.abs(grid).max()
+    return grid
+
+
 # ----------------------------------------------------------------------------------------
 # the loss
 # ----------------------------------------------------------------------------------------

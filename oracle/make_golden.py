@@ -180,11 +180,36 @@ def build_imager_case():
     print("imager: ok")
 
 
+def build_voxel_case():
+    """Voxel grid of the reference loader (src/loader/dsec/utils.py:19-77), imported by file path
+    because the loader package pulls in h5py / hdf5plugin (absent here)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_dsec_utils", os.path.join(REF, "src/loader/dsec/utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(11)
+    C, H, W, n = 5, 24, 36, 6000
+    x = torch.rand(n) * (W + 3) - 1.5            # includes (-1, 0): int() truncates toward zero
+    y = torch.rand(n) * (H + 3) - 1.5
+    t = torch.rand(n).sort().values
+    t = (t - t[0]) / (t[-1] - t[0])
+    p = (torch.rand(n) < 0.5).float()
+    out = dict(x=x.numpy(), y=y.numpy(), t=t.numpy(), p=p.numpy(), shape=np.array([C, H, W]))
+    for norm in (None, "mean_std", "max"):
+        vg = mod.VoxelGrid((C, H, W), norm, 0)
+        out["grid_" + str(norm)] = vg.convert({"p": p, "t": t, "x": x, "y": y}).numpy()
+    vg = mod.VoxelGrid((C, H, W), "mean_std", 0.05)
+    out["grid_mean_std_q05"] = vg.convert({"p": p, "t": t, "x": x, "y": y}).numpy()
+    np.savez_compressed(os.path.join(OUT, "voxel.npz"), **out)
+    print("voxel: ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for i, (name, (cfg, opt)) in enumerate(CASES.items()):
         build_case(name, cfg, opt, seed=100 + i)
     build_imager_case()
+    build_voxel_case()
 
 
 if __name__ == "__main__":

@@ -103,3 +103,11 @@ def test_knn_ties_pick_lowest_index():
     ind, dist = fo.knn_bruteforce(pos, grid, 2, "l2")
     assert (dist[..., 0] == dist[..., 1]).all() is not None
     assert (ind[..., 0] < ind[..., 1])[dist[..., 0] == dist[..., 1]].all()
+
+
+def test_voxel_grid_oracle_matches_reference():
+    z = np.load(f"{GOLDEN_DIR}/voxel.npz")
+    shape = tuple(int(v) for v in z["shape"])
+    for norm in (None, "mean_std", "max"):
+        got = fo.voxel_grid(z["x"], z["y"], z["t"], z["p"], shape, norm)
+        assert rel_err(got, z["grid_" + str(norm)]) < 2e-6, norm
