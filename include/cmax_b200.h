@@ -39,6 +39,7 @@ enum { CMAX_NORM_L1 = 0, CMAX_NORM_L2 = 1 };
 enum { CMAX_INTERP_MEAN = 0, CMAX_INTERP_IWD = 1 };
 enum { CMAX_SMOOTH_ON_FLOW_TO_TREF = 0, CMAX_SMOOTH_ON_FLOW_TO_NEXT = 1 };
 enum { CMAX_BASIS_POLYNOMIAL = 0, CMAX_BASIS_DCT = 1, CMAX_BASIS_BEZIER = 2 };
+enum { CMAX_FOCUS_GRADIENT_MAGNITUDE = 0, CMAX_FOCUS_VARIANCE = 1 };
 
 /* Mirrors the keyword arguments of upstream FocusLoss.__init__ (src/losses/focus.py:28-51). */
 typedef struct CmaxConfig {
@@ -57,7 +58,9 @@ typedef struct CmaxConfig {
     float smooth_weight;
     int32_t deterministic;            /* 1: IWE and LUT-gradient accumulate in int64 fixed point
                                          (run-to-run bit-identical); 0: float32 atomics          */
-    int32_t reserved[3];
+    int32_t focus_functional;         /* CMAX_FOCUS_GRADIENT_MAGNITUDE (what upstream calc hard-codes,
+                                         focus.py:90) | CMAX_FOCUS_VARIANCE (loss.py:14-16)       */
+    int32_t reserved[2];
 } CmaxConfig;
 
 int cmax_abi_version(void);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG, "_lib", "libcmax_b200.so")
 NORM = {"l1": 0, "l2": 1}
 INTERP = {"mean": 0, "iwd": 1}
 SMOOTH = {"on_flow_to_tref": 0, "on_flow_to_next": 1}
+FOCUS = {"gradient_magnitude": 0, "variance": 1}        # upstream src/utils/loss.py:4-12
 
 EXPORTS = (
     "cmax_abi_version", "cmax_error_string", "cmax_workspace_bytes", "cmax_forward",
@@ -33,7 +34,7 @@ class CmaxConfig(Structure):
         ("dist_norm", c_int32), ("scale_iwe_by_dt", c_int32), ("mask_image_border", c_int32),
         ("polarity_aware_batching", c_int32), ("interpolation_scheme", c_int32),
         ("smooth_type", c_int32), ("smooth_weight", c_float), ("deterministic", c_int32),
-        ("reserved", c_int32 * 3),
+        ("focus_functional", c_int32), ("reserved", c_int32 * 2),
     ]
 
 
@@ -109,7 +110,7 @@ def check(rc: int, what: str) -> None:
 def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_superpixel_size,
                 focus_loss_norm, dist_norm, scale_iwe_by_dt, mask_image_border,
                 polarity_aware_batching, interpolation_scheme, smooth_type,
-                deterministic=False) -> CmaxConfig:
+                deterministic=False, focus_loss_type="gradient_magnitude") -> CmaxConfig:
     for name, table, val in (("focus_loss_norm", NORM, focus_loss_norm),
                              ("dist_norm", NORM, dist_norm),
                              ("interpolation_scheme", INTERP, interpolation_scheme),
@@ -128,6 +129,9 @@ def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_sup
     c.smooth_type = SMOOTH[smooth_type]
     c.smooth_weight = float(smooth_weight)
     c.deterministic = int(bool(deterministic))
+    if focus_loss_type not in FOCUS:
+        raise ValueError(f"focus_loss_type={focus_loss_type!r} not in {sorted(FOCUS)}")
+    c.focus_functional = FOCUS[focus_loss_type]
     return c
 
 

@@ -96,7 +96,8 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
         c->lut_superpixel_size < 1)
         return CMAX_ERR_BAD_CONFIG;
     if ((unsigned)c->focus_loss_norm > 1u || (unsigned)c->dist_norm > 1u ||
-        (unsigned)c->interpolation_scheme > 1u || (unsigned)c->smooth_type > 1u)
+        (unsigned)c->interpolation_scheme > 1u || (unsigned)c->smooth_type > 1u ||
+        (unsigned)c->focus_functional > 1u)
         return CMAX_ERR_BAD_CONFIG;
     // focus.py:49-51
     if (c->num_tref != 1 && (c->scale_iwe_by_dt || c->polarity_aware_batching ||
@@ -121,6 +122,7 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     g->iwd = c->interpolation_scheme == CMAX_INTERP_IWD && c->num_knn > 1;    // focus.py:145-163
     g->smooth_next = c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT;
     g->det = c->deterministic != 0;
+    g->variance = c->focus_functional == CMAX_FOCUS_VARIANCE;
     g->smooth_w = c->smooth_weight;
     g->B = B;
     g->M = M;
@@ -178,7 +180,8 @@ Layout make_layout(const Geom &g)
     const int64_t sm_imgs = g.smooth_next ? g.B * (g.nb - 1) : g.S * g.R;
     L.n_sm_blocks = (int)(sm_imgs * ((g.Wq + 31) / 32) * ((g.Hq + 7) / 8));
     L.header = take(1024);
-    L.focus_partials = take(sizeof(double) * L.n_img_blocks);
+    L.focus_partials = take(sizeof(double) * 2 * L.n_img_blocks);   // [sum | sum of squares]
+    L.plane_stats = take(sizeof(double) * 2 * planes);              // per plane: mean, variance
     L.smooth_partials = take(sizeof(double) * (L.n_sm_blocks > 0 ? L.n_sm_blocks : 1));
     take_knn(g, L, take);
     L.bpart = take(sizeof(float2) * g.S * g.n * (g.R + (g.smooth_next ? 1 : 0)));

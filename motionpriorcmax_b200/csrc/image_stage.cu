@@ -35,7 +35,7 @@ constexpr int T = kImgTile;
 // ---- forward: blur + sobel + partial focus sum ------------------------------------------------
 __global__ void __launch_bounds__(256)
 image_forward_kernel(const float *__restrict__ raw, float *__restrict__ blurred_out, int H, int W,
-                     Gauss3 gk, int l2, double *__restrict__ partials)
+                     Gauss3 gk, int l2, int variance, double *__restrict__ partials, int n_blocks)
 {
     __shared__ float s_raw[T + 4][T + 4 + 1];
     __shared__ float s_blur[T + 2][T + 2 + 1];
@@ -70,7 +70,7 @@ image_forward_kernel(const float *__restrict__ raw, float *__restrict__ blurred_
         s_blur[ly][lx] = v;
     }
     __syncthreads();
-    double acc = 0.0;
+    double acc = 0.0, acc2 = 0.0;
     float *outp = blurred_out + plane * (int64_t)H * W;
     for (int i = tid; i < T * T; i += 256) {
         int ly = i / T, lx = i - ly * T;
@@ -81,13 +81,19 @@ image_forward_kernel(const float *__restrict__ raw, float *__restrict__ blurred_
             const float g_ = s_blur[ly + 2][lx], h = s_blur[ly + 2][lx + 1], k = s_blur[ly + 2][lx + 2];
             const float dx = (c - a) + 2.0f * (f - d) + (k - g_);
             const float dy = (g_ - a) + 2.0f * (h - b) + (k - c);
-            acc += l2 ? (double)(dx * dx + dy * dy) : (double)(fabsf(dx) + fabsf(dy));
-            outp[(int64_t)yy * W + xx] = s_blur[ly + 1][lx + 1];
+            const float v = s_blur[ly + 1][lx + 1];
+            if (variance) { acc += (double)v; acc2 += (double)v * (double)v; }     // loss.py:14-16
+            else acc += l2 ? (double)(dx * dx + dy * dy) : (double)(fabsf(dx) + fabsf(dy));
+            outp[(int64_t)yy * W + xx] = v;
         }
     }
     acc = block_sum(acc, s_red);
-    if (tid == 0)
-        partials[(plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
+    if (variance) acc2 = block_sum(acc2, s_red);
+    if (tid == 0) {
+        const int64_t idx = (plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partials[idx] = acc;
+        partials[n_blocks + idx] = acc2;
+    }
 }
 
 // plain blur for the stand-alone imager
@@ -112,7 +118,7 @@ blur_kernel(const float *__restrict__ raw, float *__restrict__ out, int H, int W
 // D' = blur^T( Sobel_x^T u + Sobel_y^T v ),  (u, v) = (sign dx, sign dy)  [l1]  or (2dx, 2dy) [l2]
 __global__ void __launch_bounds__(256)
 image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, int H, int W,
-                      Gauss3 gk, int l2)
+                      Gauss3 gk, int l2, int variance, const double *__restrict__ plane_stats)
 {
     __shared__ float s_raw[T + 8][T + 8 + 1];
     __shared__ float s_blur[T + 6][T + 6 + 1];
@@ -148,7 +154,18 @@ image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, i
         s_blur[ly][lx] = v;
     }
     __syncthreads();
-    for (int i = tid; i < (T + 4) * (T + 4); i += 256) {
+    if (variance) {
+        // d var / d blurred = 2 (I - mean) / (Np - 1); the event stage multiplies by
+        // grad * (-1/val^2) / (planes * Np), so G carries the factor Np / (Np - 1)
+        const float mean = (float)plane_stats[2 * plane];
+        const float c = 2.0f * (float)((double)H * W / ((double)H * W - 1.0));
+        for (int i = tid; i < (T + 2) * (T + 2); i += 256) {
+            int ly = i / (T + 2), lx = i - ly * (T + 2);
+            int yy = y0 + ly - 1, xx = x0 + lx - 1;
+            s_g[ly][lx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? c * (s_blur[ly + 2][lx + 2] - mean) : 0.0f;
+        }
+    }
+    for (int i = tid; i < (variance ? 0 : (T + 4) * (T + 4)); i += 256) {
         int ly = i / (T + 4), lx = i - ly * (T + 4);
         int yy = y0 + ly - 2, xx = x0 + lx - 2;
         float u = 0.0f, v = 0.0f;                         // outside the image: no Sobel output
@@ -169,7 +186,7 @@ image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, i
     }
     __syncthreads();
     // G = Sobel_x^T u + Sobel_y^T v on tile + halo 1 (positions outside the image are unused)
-    for (int i = tid; i < (T + 2) * (T + 2); i += 256) {
+    for (int i = tid; i < (variance ? 0 : (T + 2) * (T + 2)); i += 256) {
         int ly = i / (T + 2), lx = i - ly * (T + 2);
         // G[i,j] = sum_{a,b} SX[a,b] u[i-a+1, j-b+1] + SY[a,b] v[i-a+1, j-b+1]
         const float (*U)[T + 4 + 1] = s_u;
@@ -340,16 +357,32 @@ smooth_backward_kernel(const float *__restrict__ field, int Hq, int Wq, int Rv,
 __global__ void __launch_bounds__(256)
 finalize_losses_kernel(Header *hdr, const double *__restrict__ fpart, int nf,
                        const double *__restrict__ spart, int ns, double n_pix, double n_smooth,
-                       float smooth_w, float *__restrict__ losses_out)
+                       float smooth_w, int variance, int planes, double *__restrict__ plane_stats,
+                       float *__restrict__ losses_out)
 {
     __shared__ double s_red[32];
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nf; i += 256) a += fpart[i];
+    if (variance) {
+        // per plane: mean and unbiased variance over H*W (torch.var, loss.py:14-16)
+        const int per = nf / planes;
+        const double np_ = n_pix / planes;
+        for (int p = threadIdx.x; p < planes; p += 256) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int i = 0; i < per; ++i) { s1 += fpart[p * per + i]; s2 += fpart[nf + p * per + i]; }
+            plane_stats[2 * p] = s1 / np_;
+            plane_stats[2 * p + 1] = (s2 - s1 * s1 / np_) / (np_ - 1.0);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int p = 0; p < planes; ++p) a += plane_stats[2 * p + 1];     // fixed order
+    } else {
+        for (int i = threadIdx.x; i < nf; i += 256) a += fpart[i];
+        a = block_sum(a, s_red);
+    }
     for (int i = threadIdx.x; i < ns; i += 256) b += spart[i];
-    a = block_sum(a, s_red);
     b = block_sum(b, s_red);
     if (threadIdx.x == 0) {
-        const float val = (float)(a / n_pix);                        // torch.mean (loss.py:23-25)
+        const float val = variance ? (float)(a / planes) : (float)(a / n_pix);   // torch.mean
         const float focus = 1.0f / val;                              // loss.py:12
         float smooth = 0.0f;
         if (ns > 0 && n_smooth > 0) smooth = smooth_w * (float)(b / n_smooth / 2.0);
@@ -385,7 +418,7 @@ int launch_image_forward(const Geom &g, const Layout &L, char *ws, float *iwes_o
     count_launch();
     image_forward_kernel<<<grid, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const float *>(ws + L.raw), iwes_out, g.H, g.W, gauss3(1.0f), g.l2focus,
-        reinterpret_cast<double *>(ws + L.focus_partials));
+        g.variance, reinterpret_cast<double *>(ws + L.focus_partials), L.n_img_blocks);
     return check_launch();
 }
 
@@ -397,7 +430,7 @@ int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t
     count_launch();
     image_backward_kernel<<<grid, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const float *>(ws + L.raw), reinterpret_cast<float *>(ws + L.dimg), g.H,
-        g.W, gauss3(1.0f), g.l2focus);
+        g.W, gauss3(1.0f), g.l2focus, g.variance, reinterpret_cast<const double *>(ws + L.plane_stats));
     return check_launch();
 }
 
@@ -476,7 +509,7 @@ int launch_finalize_losses(const Geom &g, const Layout &L, char *ws, float *loss
         reinterpret_cast<Header *>(ws + L.header),
         reinterpret_cast<const double *>(ws + L.focus_partials), L.n_img_blocks,
         reinterpret_cast<const double *>(ws + L.smooth_partials), ns, n_pix, n_smooth, g.smooth_w,
-        losses_out);
+        g.variance, (int)(g.B * g.R * g.P), reinterpret_cast<double *>(ws + L.plane_stats), losses_out);
     return check_launch();
 }
 

@@ -91,13 +91,15 @@ class FocusLoss(base.TrajectoryLossBase):
         interpolation_scheme (str): 'mean' or 'iwd'.
         smooth_type (str): 'on_flow_to_tref' or 'on_flow_to_next'.
     Extra (optional, new): deterministic (bool) - int64 fixed-point IWE / LUT-gradient
-        accumulation, run-to-run bit-identical.
+        accumulation, run-to-run bit-identical; focus_loss_type ('gradient_magnitude' as upstream
+        calc hard-codes, or 'variance' = upstream utils.calculate_focus_loss(loss_type='variance')).
     """
 
     def __init__(self, image_shape, num_tref, num_bins, num_knn, smooth_weight,
                  lut_superpixel_size, focus_loss_norm, dist_norm,
                  scale_iwe_by_dt, mask_image_border, polarity_aware_batching,
-                 interpolation_scheme, smooth_type, deterministic=False, **kwargs):
+                 interpolation_scheme, smooth_type, deterministic=False,
+                 focus_loss_type='gradient_magnitude', **kwargs):
         super().__init__()
         self.image_shape = tuple(image_shape)
         self.num_tref = num_tref
@@ -113,6 +115,7 @@ class FocusLoss(base.TrajectoryLossBase):
         self.interpolation_scheme = interpolation_scheme
         self.smooth_type = smooth_type
         self.deterministic = bool(deterministic)
+        self.focus_loss_type = focus_loss_type      # upstream calc hard-codes 'gradient_magnitude' (focus.py:90)
         self.is_needing_offsets = True
         self.imager = EventImageConverter(self.image_shape, deterministic=self.deterministic)
 
@@ -129,7 +132,7 @@ class FocusLoss(base.TrajectoryLossBase):
             self.image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_superpixel_size,
             focus_loss_norm, dist_norm, scale_iwe_by_dt, mask_image_border,
             polarity_aware_batching, interpolation_scheme if num_knn > 1 else 'mean', smooth_type,
-            self.deterministic)
+            self.deterministic, focus_loss_type)
         cabi.load()      # fail at construction time when the CUDA library is missing
 
     def get_reconstruction_times(self, device):

@@ -417,6 +417,7 @@ class FocusOracle:
     smooth_type: str
     dtype: type = np.float32
     use_c_knn: bool = True
+    focus_loss_type: str = "gradient_magnitude"      # upstream calc hard-codes it (focus.py:90)
     ctx: dict = field(default_factory=dict, repr=False)
 
     def __post_init__(self):
@@ -519,7 +520,9 @@ class FocusOracle:
 
         # ---- focus (loss.py:4-27)
         dx, dy = sobel(iwes)
-        if self.focus_loss_norm == "l2":
+        if self.focus_loss_type == "variance":               # loss.py:14-16: mean of unbiased var
+            val = np.mean(np.var(iwes.astype(np.float64), axis=(-2, -1), ddof=1))
+        elif self.focus_loss_norm == "l2":
             val = np.mean(dx * dx + dy * dy, dtype=np.float64)
         elif self.focus_loss_norm == "l1":
             val = np.mean(np.abs(dx) + np.abs(dy), dtype=np.float64)
@@ -548,7 +551,7 @@ class FocusOracle:
         loss = focus + smooth
 
         self.ctx = dict(B=B, R=R, P=P, M=M, n=n, nb=nb, q=q, Hq=Hq, Wq=Wq, ind_k=ind_k, wk=wk,
-                        it=it, iy=iy, ix=ix, warped=wy_flat, w=w_flat, dx=dx, dy=dy, val=val,
+                        it=it, iy=iy, ix=ix, warped=wy_flat, w=w_flat, dx=dx, dy=dy, val=val, iwes=iwes,
                         sm_field=sm_field, npos=int(num_pos_events), mean_div=mean_div)
         if sm_field is not None:
             self.ctx.update(sdx=sdx, sdy=sdy, cx=cx, cy=cy)
@@ -567,11 +570,19 @@ class FocusOracle:
         # focus -> blurred IWE
         N = c["dx"].size
         coef = dt_(grad_loss) * (-(dt_(1) / (c["val"] * c["val"]))) / dt_(N)
-        if self.focus_loss_norm == "l1":
+        if self.focus_loss_type == "variance":
+            I = c["iwes"]
+            npix = H * W
+            planes = I.shape[0] * I.shape[1]
+            mean = I.mean(axis=(-2, -1), keepdims=True, dtype=np.float64)
+            d_blur = (dt_(grad_loss) * (-(dt_(1) / (c["val"] * c["val"]))) / dt_(planes)
+                      * 2 * (I - mean) / (npix - 1)).astype(dt_)
+        elif self.focus_loss_norm == "l1":
             gdx, gdy = coef * np.sign(c["dx"]), coef * np.sign(c["dy"])
+            d_blur = sobel_T(gdx.astype(dt_), gdy.astype(dt_))
         else:
             gdx, gdy = coef * 2 * c["dx"], coef * 2 * c["dy"]
-        d_blur = sobel_T(gdx.astype(dt_), gdy.astype(dt_))
+            d_blur = sobel_T(gdx.astype(dt_), gdy.astype(dt_))
         D = blur_T(d_blur, 1.0)                                          # dL/d raw IWE [B*R,P,H,W]
 
         # raw IWE -> warped coordinates -> LUT (event_image_converter.py:382-386)

@@ -69,6 +69,9 @@ CASES = {
     "s2_patch2_iwd": (cfgv(image_shape=(16, 24), lut_superpixel_size=2, num_knn=9,
                            interpolation_scheme="iwd"),
                       dict(B=2, M=300, K=1, basis="polynomial", patch=2)),
+    # the reference's other focus functional (src/utils/loss.py:14-16); FocusLoss.calc hard-codes
+    # 'gradient_magnitude' (focus.py:90), so the call is redirected for this case only
+    "variance_functional": (cfgv(), dict(B=2, M=700, K=1, basis="polynomial", patch=4, variance=True)),
 }
 
 
@@ -137,10 +140,18 @@ def build_case(name, cfg, opt, seed):
         cap["lut"], cap["next"] = lut, nxt
         return lut, nxt
     L.interpolate_flow = wrapped
-    loss, log, misc = L.calc(traj, times, batch)
+    import src.losses.focus as ref_focus
+    orig_focus = ref_focus.utils.calculate_focus_loss
+    if opt.get("variance"):
+        ref_focus.utils.calculate_focus_loss = lambda iw, loss_type, norm: orig_focus(iw, loss_type="variance", norm=norm)
+    try:
+        loss, log, misc = L.calc(traj, times, batch)
+    finally:
+        ref_focus.utils.calculate_focus_loss = orig_focus
     loss.backward()
     out = dict(
-        cfg=json.dumps(cfg), trajectories=traj.detach().numpy(), times=times.numpy(),
+        cfg=json.dumps(dict(cfg, focus_loss_type="variance") if opt.get("variance") else cfg),
+        trajectories=traj.detach().numpy(), times=times.numpy(),
         events=ev.numpy(), num_pos_events=np.int64(-1 if npos is None else npos),
         loss=loss.detach().numpy(), focus_loss=log["focus_loss"].numpy(),
         smoothness_loss=log["smoothness_loss"].numpy(), iwes=misc["iwes"].numpy(),
