@@ -145,6 +145,14 @@ int cmax_voxel_grid(const float *x, const float *y, const float *t, const float 
                     int32_t C, int32_t H, int32_t W, int32_t norm_type, float *grid_out,
                     double *stats_scratch, void *stream);
 
+/* Dense flow read-out, upstream dense_flow_from_traj (src/utils/flow.py:8-16): list_to_grid
+ * (src/utils/trajectories.py:54-75) on the patch lattice, then torchvision BICUBIC antialias
+ * resize to the image.  traj_flow [B, n, C], pixel_positions [n, 2] int64 (y, x);
+ * patch_flow_out [B, C, H/patch, W/patch], dense_out [B, C, H, W].  Forward only. */
+int cmax_dense_flow(const float *traj_flow, const int64_t *pixel_positions, int64_t B, int64_t n,
+                    int32_t C, int32_t patch, int32_t H, int32_t W, float *patch_flow_out,
+                    float *dense_out, void *stream);
+
 /* Micro-benchmark used by bench.py to measure the atomic side of the roofline on the box:
  * n_ops float32 `red.global.add` to pseudo-random addresses inside `region_floats` floats.
  * mode 0: global red.f32, 1: shared-memory atomics + flush, 2: global red on int64. */

@@ -23,7 +23,7 @@ EXPORTS = (
     "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
     "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
-    "cmax_last_worklist_count", "cmax_voxel_grid",
+    "cmax_last_worklist_count", "cmax_voxel_grid", "cmax_dense_flow",
 )
 
 
@@ -81,6 +81,8 @@ def load():
                                                c_int32, c_int32, c_int32, P, P]
     lib.cmax_voxel_grid.restype = c_int32
     lib.cmax_voxel_grid.argtypes = [P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P]
+    lib.cmax_dense_flow.restype = c_int32
+    lib.cmax_dense_flow.argtypes = [P, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P]
     lib.cmax_atomic_microbench.restype = c_int32
     lib.cmax_atomic_microbench.argtypes = [P, c_int64, c_int64, c_int32, P]
     lib.cmax_read_status.restype = c_int32

@@ -369,6 +369,43 @@ def create_iwe(events, image_shape, weight=1.0, sigma=1, dtype=np.float32) -> np
     return blur(img, sigma) if sigma > 0 else img
 
 
+def _cubic_aa(x, a=-0.5):
+    x = np.abs(x)
+    return np.where(x < 1, ((a + 2) * x - (a + 3)) * x * x + 1, np.where(x < 2, a * (((x - 5) * x + 8) * x - 4), 0.0))
+
+
+def resize_bicubic_antialias(img, out_h, out_w):
+    """torchvision resize(BICUBIC, antialias=True) = ATen's separable anti-aliased bicubic
+    (last dimension first); img [..., h, w] -> [..., out_h, out_w]."""
+    def weights(n_in, n_out):
+        scale = n_in / n_out
+        support = 2.0 * scale if scale >= 1 else 2.0
+        inv = 1.0 / scale if scale >= 1 else 1.0
+        out = []
+        for i in range(n_out):
+            c = scale * (i + 0.5)
+            lo = max(int(c - support + 0.5), 0)
+            cnt = min(int(c + support + 0.5), n_in) - lo
+            w = _cubic_aa((np.arange(cnt) + lo - c + 0.5) * inv)
+            out.append((lo, w / w.sum()))
+        return out
+    img = np.asarray(img, np.float64)
+    wx, wy = weights(img.shape[-1], out_w), weights(img.shape[-2], out_h)
+    tmp = np.stack([(img[..., :, lo:lo + len(w)] * w).sum(-1) for lo, w in wx], -1)
+    return np.stack([(tmp[..., lo:lo + len(w), :] * w[:, None]).sum(-2) for lo, w in wy], -2)
+
+
+def dense_flow_from_traj(traj_flow, pixel_positions, patch, image_shape):
+    """src/utils/flow.py:12-16 + list_to_grid (src/utils/trajectories.py:54-75)."""
+    h, w = image_shape
+    tf = np.asarray(traj_flow, np.float64)
+    b, n, c = tf.shape
+    grid = np.zeros((b, c, h // patch, w // patch))
+    pos = np.asarray(pixel_positions) // patch
+    grid[:, :, pos[:, 0], pos[:, 1]] = tf.transpose(0, 2, 1)
+    return resize_bicubic_antialias(grid, h, w), grid
+
+
 def voxel_grid(x, y, t, p, shape, norm_type=None):
     """src/loader/dsec/utils.py:29-77 (VoxelGrid.convert, quantile == 0): trilinear vote of 2p-1,
     int() truncation toward zero, float32 arithmetic, then 'mean_std' / 'max' normalisation."""

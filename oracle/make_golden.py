@@ -215,12 +215,28 @@ def build_voxel_case():
     print("voxel: ok")
 
 
+def build_dense_flow_case():
+    """Dense flow read-out of the reference (src/utils/flow.py:12-16)."""
+    from src.utils import flow as ref_flow
+    torch.manual_seed(5)
+    H, W, patch = 24, 32, 4
+    mask = ref_traj.get_optical_flow_tile_mask((H, W), patch)
+    pos = torch.nonzero(mask)
+    tf = torch.randn(2, len(pos), 2) * 5
+    dense, patch_flow = ref_flow.dense_flow_from_traj(tf, pos, patch, (H, W))
+    np.savez_compressed(os.path.join(OUT, "dense_flow.npz"), traj_flow=tf.numpy(), pixel_positions=pos.numpy(),
+                        patch=np.int64(patch), shape=np.array([H, W]), dense=dense.numpy(),
+                        patch_flow=patch_flow.numpy())
+    print("dense_flow: ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for i, (name, (cfg, opt)) in enumerate(CASES.items()):
         build_case(name, cfg, opt, seed=100 + i)
     build_imager_case()
     build_voxel_case()
+    build_dense_flow_case()
 
 
 if __name__ == "__main__":

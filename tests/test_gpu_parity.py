@@ -583,3 +583,23 @@ def test_voxel_grid_matches_reference_golden():
     ev = {k: torch.as_tensor(v, device=dev) for k, v in (("x", x), ("y", y), ("t", t), ("p", p))}
     got = VoxelGrid((15, 480, 640), "mean_std", 0).convert(ev).cpu().numpy()
     assert rel_err(got, fo.voxel_grid(x, y, t, p, (15, 480, 640), "mean_std")) < TOL
+
+
+def test_dense_flow_readout_matches_reference_golden():
+    """list_to_grid + anti-aliased bicubic resize vs the reference."""
+    from motionpriorcmax_b200.utils import dense_flow_from_traj
+    from motionpriorcmax_b200 import trajectories as tj
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    z = np.load(f"{GOLDEN_DIR}/dense_flow.npz")
+    H, W = (int(v) for v in z["shape"])
+    dense, patch = dense_flow_from_traj(torch.as_tensor(z["traj_flow"], device=dev),
+                                        torch.as_tensor(z["pixel_positions"], device=dev), int(z["patch"]), (H, W))
+    assert np.array_equal(patch.cpu().numpy(), z["patch_flow"])
+    assert dense.shape == z["dense"].shape and rel_err(dense.cpu().numpy(), z["dense"]) < TOL
+    # DSEC size (scripts/dsec_inference.py:85-93) against the oracle restatement
+    pos = tj.tile_positions((480, 640), 4)
+    tf = torch.randn(1, len(pos), 2, device=dev) * 10
+    dense, patch = dense_flow_from_traj(tf, pos, 4, (480, 640))
+    ref, _ = fo.dense_flow_from_traj(tf.cpu().numpy(), pos.numpy(), 4, (480, 640))
+    assert rel_err(dense.cpu().numpy(), ref) < TOL

@@ -111,3 +111,11 @@ def test_voxel_grid_oracle_matches_reference():
     for norm in (None, "mean_std", "max"):
         got = fo.voxel_grid(z["x"], z["y"], z["t"], z["p"], shape, norm)
         assert rel_err(got, z["grid_" + str(norm)]) < 2e-6, norm
+
+
+def test_dense_flow_oracle_matches_reference():
+    z = np.load(f"{GOLDEN_DIR}/dense_flow.npz")
+    H, W = (int(v) for v in z["shape"])
+    dense, patch = fo.dense_flow_from_traj(z["traj_flow"], z["pixel_positions"], int(z["patch"]), (H, W))
+    assert np.array_equal(patch.astype(np.float32), z["patch_flow"])
+    assert rel_err(dense, z["dense"]) < 1e-6
