@@ -36,28 +36,28 @@ def _run_loss(cfg, traj, times, events, npos, deterministic=False, grad_scale=1.
                 dtraj=t.grad.cpu().numpy(), loss_t=loss)
 
 
-def _assert_grad_close(got, truth64, cfg, traj, times, ev, npos, tol=2 * TOL):
+def _assert_grad_close(got, truth64, cfg, traj, times, ev, npos, tol=2 * TOL, gpu_iwes=None):
     """Norm-wise 1e-5-class check of d loss / d trajectories.
 
     With the l1 focus norm the gradient contains sign(Sobel response).  A pixel whose response
     is ~0 flips its sign between float64, float32 and float32-with-another-summation-order
-    (SURVEY.md section 7 "hard parts"; float atomics make the order vary run to run), which moves
-    the gradient of the few trajectories near that pixel by far more than rounding.  For l1 the
-    check therefore is: either the strict norm-wise bound holds, or the float32 oracle (same
-    arithmetic as the reference) is matched, or the disagreement is confined to a handful of
-    entries (< 0.2 %) with a small norm-wise footprint."""
+    (SURVEY.md section 7 "hard parts"; float atomics make the order vary run to run), and one
+    flipped pixel moves the gradient of every trajectory interpolated from its neighbourhood by
+    far more than rounding.  So when the strict bound fails for l1, the oracle's backward is
+    re-evaluated with the sign pattern of the *GPU's own* blurred IWE (which is itself verified
+    to 1e-5): everything downstream of the sign must then agree to the same strict bound."""
     from oracle import focus_oracle as fo
     e64 = rel_err(got, truth64)
     if e64 < tol:
         return
-    assert cfg["focus_loss_norm"] == "l1", e64
-    o32 = fo.FocusOracle(**cfg, dtype=np.float32)
-    o32.forward(traj, times, ev, npos)
-    if rel_err(got, o32.backward()["dtraj"]) < tol:
-        return
-    scale = np.abs(truth64).max()
-    bad = np.abs(np.asarray(got, np.float64) - truth64) > 1e-4 * scale
-    assert bad.mean() < 2e-3 and e64 < 2e-2, (e64, float(bad.mean()))
+    assert cfg["focus_loss_norm"] == "l1" and cfg.get("focus_loss_type", "gradient_magnitude") != "variance", e64
+    assert gpu_iwes is not None, e64
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    o.forward(traj, times, ev, npos)
+    dx, dy = fo.sobel(np.asarray(gpu_iwes, np.float64).reshape(o.ctx["dx"].shape))
+    o.ctx["dx"], o.ctx["dy"] = dx, dy
+    e = rel_err(got, o.backward()["dtraj"])
+    assert e < tol, (e64, e)
 
 
 # ------------------------------------------------------------------------------------------
@@ -77,7 +77,8 @@ def test_loss_matches_reference_golden(name, deterministic):
     assert r["lut"].shape == c["flow_lut"].shape
     assert rel_err(r["lut"], c["flow_lut"]) < TOL
     assert r["dtraj"].shape == c["dtraj"].shape
-    assert rel_err(r["dtraj"], c["dtraj"]) < TOL
+    _assert_grad_close(r["dtraj"], c["dtraj"], c["cfg"], c["trajectories"], c["times"], c["events"],
+                       c["num_pos_events"], tol=TOL, gpu_iwes=r["iwes"])
 
 
 def test_imager_matches_reference_golden():
@@ -215,7 +216,8 @@ def test_zero_flow_lattice_ties():
     g = o.backward()
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert np.abs(r["lut"]).max() == 0.0
-    assert rel_err(r["dtraj"], g["dtraj"]) < TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, c["times"], c["events"], c["num_pos_events"],
+                       tol=TOL, gpu_iwes=r["iwes"])
 
 
 # ------------------------------------------------------------------------------------------
@@ -257,7 +259,7 @@ def test_loss_matches_oracle_midsize(variant):
     assert abs(r["smooth"] - f["smoothness_loss"]) <= TOL * max(abs(f["smoothness_loss"]), 1e-3)
     assert rel_err(r["iwes"], f["iwes"]) < TOL
     assert rel_err(r["lut"], f["flow_lut"]) < TOL
-    _assert_grad_close(r["dtraj"], g["dtraj"], base, traj, times, ev, npos)
+    _assert_grad_close(r["dtraj"], g["dtraj"], base, traj, times, ev, npos, gpu_iwes=r["iwes"])
 
 
 def test_deterministic_mode_is_bit_reproducible_and_close():
@@ -313,7 +315,7 @@ def test_full_size_dsec_window_matches_oracle():
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(r["iwes"], f["iwes"]) < TOL
     assert rel_err(r["lut"], f["flow_lut"]) < TOL
-    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos)
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos, gpu_iwes=r["iwes"])
 
 
 def test_properties_at_full_size():
@@ -360,7 +362,7 @@ def test_edge_cases_empty_and_tiny():
     f = o.forward(traj, times, ev, npos)
     g = o.backward()
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
-    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos, gpu_iwes=r["iwes"])
     # K == n (every trajectory is a neighbour of every cell)
     cfg2 = dict(cfg, num_knn=traj.shape[2])
     r2 = _run_loss(cfg2, traj, times, ev, npos)
@@ -444,7 +446,7 @@ def test_many_free_trajectories_large_n():
     g = o.backward()
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(r["lut"], f["flow_lut"]) < TOL
-    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev.numpy(), npos)
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev.numpy(), npos, gpu_iwes=r["iwes"])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -492,9 +494,13 @@ def test_full_size_evimo2_bezier_window_matches_oracle():
     assert rel_err(misc["flow_lut"].cpu().numpy(), f["flow_lut"]) < TOL
     assert rel_err(misc["iwes"].cpu().numpy(), f["iwes"]) < TOL
     e = rel_err(cgd.grad.cpu().numpy(), dcg)
-    assert e < 5e-3 if cfg["focus_loss_norm"] == "l1" else e < 2 * TOL, e
-    scale = np.abs(dcg).max()
-    assert (np.abs(cgd.grad.cpu().numpy() - dcg) > 1e-4 * scale).mean() < 2e-3
+    if e >= 2 * TOL:          # l1: sign(~0 Sobel response) flipped somewhere - see _assert_grad_close
+        dx, dy = fo.sobel(misc["iwes"].cpu().numpy().astype(np.float64).reshape(o.ctx["dx"].shape))
+        o.ctx["dx"], o.ctx["dy"] = dx, dy
+        dcg = fo.trajectories_backward(o.backward()["dtraj"], times, 4, deg, "bezier", tuple(cg.shape),
+                                       xy_order=True)
+        e = rel_err(cgd.grad.cpu().numpy(), dcg)
+    assert e < 2 * TOL, e
 
 
 def test_k3_polynomial_deterministic_mode_full_size():
@@ -514,7 +520,7 @@ def test_k3_polynomial_deterministic_mode_full_size():
     g = o.backward()
     assert abs(a["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(a["iwes"], f["iwes"]) < TOL and rel_err(a["lut"], f["flow_lut"]) < TOL
-    _assert_grad_close(a["dtraj"], g["dtraj"], cfg, traj, times, ev, npos)
+    _assert_grad_close(a["dtraj"], g["dtraj"], cfg, traj, times, ev, npos, gpu_iwes=a["iwes"])
 
 
 def test_ten_reference_times():
