@@ -76,6 +76,7 @@ def make_inputs(cfg, w, rank: int):
         counts = [int(w["median"])] * B
     ev, npos = synthetic.make_event_batch(B, counts, H, W, cfg["num_bins"],
                                           cfg["polarity_aware_batching"], seed=1234, rank=rank,
+                                          dist=w.get("dist", "uniform"),
                                           integer_coords=w.get("integer", False), coord_scale=0.8)
     cg = synthetic.make_coeff_grid(B, w["K"], H, W, sigma_px=8.0, seed=1234 + 1000 * rank)
     n_valid = int(ev[..., 5].sum().item())
@@ -236,6 +237,9 @@ def run_ours(args):
     lib = cabi.load()
 
     cfg, w = workload(args.variant, args.batch, args.events)
+    if args.dist != "uniform":
+        w["dist"] = args.dist
+        w["name"] += "_" + args.dist
     H, W = cfg["image_shape"]
     cg_h, ev_h, npos, n_valid = make_inputs(cfg, w, rank)
     B, M = ev_h.shape[0], ev_h.shape[1]
@@ -430,6 +434,9 @@ def main():
     ap.add_argument("--variant", default="dsec", choices=["dsec", "dsec_tref5", "evimo2", "k3_det"])
     ap.add_argument("--events", type=int, default=None, help="events per window (default: lognormal ~1e6)")
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "edges"],
+                    help="spatial distribution of the synthetic events (edges = ~200 line segments, "
+                         "realistic atomic contention; SURVEY.md section 8d)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     ap.add_argument("--prof-warmup", type=int, default=None, help="override the >=3 warm-up rule (ncu runs only)")
