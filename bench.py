@@ -227,6 +227,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    if world > 1:       # N ranks generate their synthetic windows at the same time: share the cores
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
