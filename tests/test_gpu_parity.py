@@ -609,3 +609,30 @@ def test_dense_flow_readout_matches_reference_golden():
     dense, patch = dense_flow_from_traj(tf, pos, 4, (480, 640))
     ref, _ = fo.dense_flow_from_traj(tf.cpu().numpy(), pos.numpy(), 4, (480, 640))
     assert rel_err(dense.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("s,shape", [(3, (30, 45)), (5, (40, 60)), (7, (42, 63))])
+def test_non_power_of_two_superpixels_and_near_multiple_coordinates(s, shape):
+    """`y // s` on float32 is Python-style floor division (focus.py:186-187): exercised with
+    cell sizes that do not divide exactly and events a few ulp around cell boundaries."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=shape, lut_superpixel_size=s, num_knn=6, num_bins=4,
+               focus_loss_norm="l2")
+    H, W = shape
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, 6000, 1, seed=s)
+    rng = np.random.default_rng(s)
+    k = 1500
+    for b in range(2):
+        for col, lim in ((0, H), (1, W)):
+            mult = rng.integers(0, lim // s, k).astype(np.float32) * s
+            jit = rng.choice(np.array([-2e-6, -1e-6, -1e-7, 0, 1e-7, 1e-6], np.float32), k)
+            vals = np.clip(mult + jit * np.maximum(mult, 1), 0, np.nextafter(np.float32(lim), np.float32(0)))
+            ev[b, :k, col] = vals
+    r = _run_loss(cfg, traj, times, ev, npos, deterministic=True)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["iwes"], f["iwes"]) < TOL and rel_err(r["lut"], f["flow_lut"]) < TOL
+    assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL

@@ -110,3 +110,46 @@ def test_valid_prefix_lengths_match_the_valid_column():
     assert np.array_equal(got, want)
     ev2, _ = synthetic.make_event_batch(3, [50, 0, 7], 48, 64, 15, False, seed=2)
     assert valid_prefix_lengths(ev2, None)[:, 0].tolist() == [50, 0, 7]
+
+
+def test_oracle_integer_semantics_equal_torch_property():
+    """Property test (hypothesis): the oracle's integer work is bit-identical to the torch
+    expressions the reference evaluates - floor(v + 1e-6) in float32 (event_image_converter.py:357),
+    float floor division `//` and truncating `.to(int)` (focus.py:185-187)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import focus_oracle as fo
+
+    f32 = st.floats(min_value=-700.0, max_value=700.0, allow_nan=False, width=32)
+    near_int = st.builds(lambda k, e: np.float32(np.float32(k) + np.float32(e)),
+                         st.integers(-3, 650), st.sampled_from([-2e-6, -1e-6, -5e-7, -1e-7, 0.0, 1e-7, 5e-7, 1e-6, 0.5]))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.one_of(f32, near_int), min_size=2, max_size=40), st.sampled_from([1, 2, 3, 4, 5, 7, 8]))
+    def check(vals, s):
+        v = np.asarray(vals, np.float32)
+        n = len(v) // 2
+        yx = np.stack((v[:n], v[n:2 * n]), -1)[None]
+        # corners / masks
+        H, W = 480, 640
+        inds, mask, frac = fo.vote_corners(yx, (H, W))
+        t = torch.from_numpy(yx)
+        fl = torch.floor(t + 1e-6)
+        y1, x1 = fl[..., 0].long(), fl[..., 1].long()
+        ref_inds = torch.stack((x1 + y1 * W, x1 + (y1 + 1) * W, (x1 + 1) + y1 * W, (x1 + 1) + (y1 + 1) * W), -1)
+        ref_mask = torch.stack(((0 <= x1) * (x1 < W) * (0 <= y1) * (y1 < H),
+                                (0 <= x1) * (x1 < W) * (0 <= y1 + 1) * (y1 + 1 < H),
+                                (0 <= x1 + 1) * (x1 + 1 < W) * (0 <= y1) * (y1 < H),
+                                (0 <= x1 + 1) * (x1 + 1 < W) * (0 <= y1 + 1) * (y1 + 1 < H)), -1)
+        assert np.array_equal(mask, ref_mask.numpy())
+        assert np.array_equal(inds, (ref_inds * ref_mask).numpy())
+        assert np.array_equal(frac, (t - fl).numpy())
+        # LUT cell indices
+        ev = np.zeros((1, n, 6), np.float32)
+        ev[0, :, 0], ev[0, :, 1], ev[0, :, 4] = np.abs(v[:n]), np.abs(v[n:2 * n]), np.abs(v[:n]) % 15
+        it, iy, ix = fo.lut_cell_indices(ev, s)
+        te = torch.from_numpy(ev)
+        assert np.array_equal(it, te[..., 4].to(int).numpy())
+        assert np.array_equal(iy, (te[..., 0] // s).to(int).numpy())
+        assert np.array_equal(ix, (te[..., 1] // s).to(int).numpy())
+
+    check()
