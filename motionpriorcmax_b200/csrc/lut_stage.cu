@@ -296,8 +296,10 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     __shared__ int s_pj[kStageCap];
     __shared__ float2 s_fl[FUSED ? kStageCap : 1];
     __shared__ int s_cell[kWinRows][kWinCols + 1];
-    __shared__ float s_ld[kListCap][kKnnBlock];
-    __shared__ int s_li[kListCap][kKnnBlock];
+    // boundary candidates: only the staged index is kept (u16, + the slice id in bits 10..13);
+    // distances are recomputed from the staged point on demand - 40 B instead of 160 B per thread
+    // buys two more resident CTAs per SM
+    __shared__ unsigned short s_li[kListCap][kKnnBlock];
     __shared__ int s_rowbase[kWinRows + 1];
     __shared__ unsigned blk_max;
 
@@ -373,6 +375,11 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
         const int cqy = min((int)floorf(qy * g.inv_cs), g.Hc - 1);
         const int cqx = min((int)floorf(qx * g.inv_cs), g.Wc - 1);
         const float bnd = window_bound(cqy, cqx, r, g, qy, qx);
+        auto list_d = [&](int u) {                      // distance of list entry u, recomputed
+            const int i = s_li[u][tid] & 0x3ff;
+            const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+            return L1D ? __fadd_rn(fabsf(dy), fabsf(dx)) : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+        };
         if (GUESS) {
             // K-th key of the same cell in the previous bin as left by the *fast* kernel (NaN where
             // it was not settled there - then a direct neighbour's value serves as the guess)
@@ -402,7 +409,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                             ax = __fadd_rn(ax, f.y);
                         }
                     } else if (d < hi) {
-                        if (m < kListCap) { s_ld[m][tid] = d; s_li[m][tid] = i; }
+                        if (m < kListCap) s_li[m][tid] = (unsigned short)i;
                         ++m;
                     }
                 };
@@ -427,11 +434,11 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 // slice the listed candidates (kept out of the hot loop: nearly every warp
                 // iteration has *some* lane inside the bracket)
                 for (int u = 0; u < min(m, kListCap); ++u) {
-                    const int bk = bucket_of(s_ld[u][tid], lo, invw);     // 1..8
+                    const int bk = bucket_of(list_d(u), lo, invw);         // 1..8
                     const unsigned inc = 1u << ((bk & 3) << 3);
                     hlo += bk < 4 ? inc : 0u;
                     hhi += (bk >= 4 && bk < 8) ? inc : 0u;
-                    s_li[u][tid] |= bk << 16;
+                    s_li[u][tid] |= (unsigned short)(bk << 10);
                 }
                 // slice of the bracket that holds the K-th key
                 int bstar = -1, cum = below;
@@ -446,7 +453,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                     int mm = 0;
                     for (int u = 0; u < m; ++u) {
                         const int pk = s_li[u][tid];
-                        const int bk = pk >> 16, i = pk & 0xffff;
+                        const int bk = pk >> 10, i = pk & 0x3ff;
                         if (bk < bstar) {
                             if (FUSED) {
                                 const float2 f = s_fl[i];
@@ -454,9 +461,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                                 ax = __fadd_rn(ax, f.y);
                             }
                         } else if (bk == bstar) {
-                            const float d = s_ld[u][tid];
-                            s_ld[mm][tid] = d;
-                            s_li[mm][tid] = i;
+                            s_li[mm][tid] = (unsigned short)i;
                             ++mm;
                         }
                     }
@@ -515,8 +520,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                                     ax = __fadd_rn(ax, f.y);
                                 }
                             } else if (bk == bstar) {
-                                s_ld[m][tid] = d;
-                                s_li[m][tid] = i;
+                                s_li[m][tid] = (unsigned short)i;
                                 ++m;
                             }
                         }
@@ -530,10 +534,10 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
             // order the first `need` boundary candidates by (d, trajectory index)
             for (int t = 0; t < need; ++t) {
                 int best = t;
-                float bd = s_ld[t][tid];
+                float bd = list_d(t);
                 int bj = s_pj[s_li[t][tid]];
                 for (int u = t + 1; u < m; ++u) {
-                    const float du = s_ld[u][tid];
+                    const float du = list_d(u);
                     if (du < bd || (du == bd && s_pj[s_li[u][tid]] < bj)) {
                         best = u;
                         bd = du;
@@ -542,10 +546,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 }
                 const int ib = s_li[best][tid];
                 if (best != t) {
-                    s_ld[best][tid] = s_ld[t][tid];
                     s_li[best][tid] = s_li[t][tid];
-                    s_ld[t][tid] = bd;
-                    s_li[t][tid] = ib;
+                    s_li[t][tid] = (unsigned short)ib;
                 }
                 if (FUSED) {
                     const float2 f = s_fl[ib];
