@@ -284,7 +284,7 @@ __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
 //                everything below the bracket and lists the few candidates inside it.  A miss
 //                (bracket wrong, list full) sends the cell to the work list - never a wrong answer.
 template <bool L1D, bool FUSED, bool GUESS>
-__global__ void __launch_bounds__(kKnnBlock)
+__global__ void __launch_bounds__(kKnnBlock, 8)
 knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 const float4 *__restrict__ sorted_all, const float2 *__restrict__ sflow_all,
                 float *__restrict__ lut, float *__restrict__ lut_copy, float *__restrict__ tau,
@@ -295,7 +295,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     __shared__ float s_py[kStageCap], s_px[kStageCap];
     __shared__ int s_pj[kStageCap];
     __shared__ float2 s_fl[FUSED ? kStageCap : 1];
-    __shared__ int s_cell[kWinRows][kWinCols + 1];
+    __shared__ unsigned short s_cell[kWinRows][kWinCols + 1];     // local run starts (< kStageCap)
     // boundary candidates: only the staged index is kept (u16, + the slice id in bits 10..13);
     // distances are recomputed from the staged point on demand - 40 B instead of 160 B per thread
     // buys two more resident CTAs per SM
@@ -349,7 +349,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
             const int *crow = cstart + (wy0 + lr) * g.Wc + wx0;
             const int ga = __ldg(crow);
             const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base;
-            for (int lc = lane; lc <= ncol; lc += 32) s_cell[lr][lc] = __ldg(crow + lc) - ga + base;
+            for (int lc = lane; lc <= ncol; lc += 32)
+                s_cell[lr][lc] = (unsigned short)min(__ldg(crow + lc) - ga + base, kStageCap);
             for (int k = lane; k < len; k += 32) {
                 const float4 rec = __ldg(sorted + ga + k);
                 s_py[base + k] = rec.x;
