@@ -1071,15 +1071,15 @@ static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *t
                        const unsigned *tile_max, const float *dlut, const float *df2n, float2 *part)
 {
     if (g.R == 1)
-        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
+        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
     else
-        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 128, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
+        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
 }
 
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
                         float *dtraj, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.n + 127) / 128), (unsigned)g.nb, (unsigned)g.B);
+    dim3 grid((unsigned)((g.n + 63) / 64), (unsigned)g.nb, (unsigned)g.B);
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
     float2 *dtraj_part = reinterpret_cast<float2 *>(ws + L.bpart);
     const float *tau = reinterpret_cast<const float *>(ws + L.tau);
