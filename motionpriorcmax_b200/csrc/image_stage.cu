@@ -211,26 +211,36 @@ image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, i
         int ly = i / T, lx = i - ly * T;
         int yy = y0 + ly, xx = x0 + lx;
         if (yy >= H || xx >= W) continue;
-        int us[3], vs[3], nu = 1, nv = 1;
-        us[0] = yy + 1;
-        vs[0] = xx + 1;
-        if (yy == 1) us[nu++] = 0;
-        if (yy == H - 2) us[nu++] = H + 1;                 // H == 3: both alias row 1
-        if (xx == 1) vs[nv++] = 0;
-        if (xx == W - 2) vs[nv++] = W + 1;
+        // direct term (u, v) = (y + 1, x + 1): s_g is zero outside the image, so the nine taps need
+        // no bounds tests
         float acc = 0.0f;
-        for (int iu = 0; iu < nu; ++iu) {
-            for (int iv = 0; iv < nv; ++iv) {
-                const int u = us[iu], v = vs[iv];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const int gy_ = u - a;                  // image row of G
-                    if (gy_ < 0 || gy_ >= H) continue;
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) {
-                        const int gx_ = v - b;
-                        if (gx_ < 0 || gx_ >= W) continue;
-                        acc += (kk[a] * kk[b]) * s_g[gy_ - y0 + 1][gx_ - x0 + 1];
+            for (int b = 0; b < 3; ++b)
+                acc += (kk[a] * kk[b]) * s_g[ly + 2 - a][lx + 2 - b];
+        // reflect-padding aliases: padded row 0 -> image row 1, padded row H+1 -> image row H-2
+        // (same for columns); only those rows / columns take the generic path
+        if (yy == 1 || yy == H - 2 || xx == 1 || xx == W - 2) {
+            int us[3], vs[3], nu = 1, nv = 1;
+            us[0] = yy + 1;
+            vs[0] = xx + 1;
+            if (yy == 1) us[nu++] = 0;
+            if (yy == H - 2) us[nu++] = H + 1;             // H == 3: both alias row 1
+            if (xx == 1) vs[nv++] = 0;
+            if (xx == W - 2) vs[nv++] = W + 1;
+            for (int iu = 0; iu < nu; ++iu) {
+                for (int iv = 0; iv < nv; ++iv) {
+                    if (iu == 0 && iv == 0) continue;       // the direct term is already in acc
+                    const int u = us[iu], v = vs[iv];
+                    for (int a = 0; a < 3; ++a) {
+                        const int gy_ = u - a;              // image row of G
+                        if (gy_ < 0 || gy_ >= H) continue;
+                        for (int b = 0; b < 3; ++b) {
+                            const int gx_ = v - b;
+                            if (gx_ < 0 || gx_ >= W) continue;
+                            acc += (kk[a] * kk[b]) * s_g[gy_ - y0 + 1][gx_ - x0 + 1];
+                        }
                     }
                 }
             }
