@@ -12,7 +12,6 @@ int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStre
 int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
                 cudaStream_t st);
 extern const int *g_last_work_count;
-extern int g_last_work_bins;
 
 // ---------------------------------------------------------------------------------------------
 // stage timing / launch counting (single-threaded caller per process, like the reference)
@@ -573,14 +572,13 @@ int64_t cmax_launch_count(void) { return g_launches; }
 
 int64_t cmax_last_worklist_count(void *stream)
 {
-    if (!g_last_work_count || g_last_work_bins <= 0 || g_last_work_bins > 65536) return -1;
-    static int host_counts[65536];
+    // inspection hook: reads the counter inside the workspace of the most recent forward call, so
+    // it is only meaningful while that workspace is still alive
+    if (!g_last_work_count) return -1;
+    int v = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemcpyAsync(host_counts, g_last_work_count, sizeof(int) * g_last_work_bins,
-                        cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&v, g_last_work_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
-    int64_t v = 0;
-    for (int i = 0; i < g_last_work_bins; ++i) v += host_counts[i];
     return v;
 }
 

@@ -938,7 +938,6 @@ lut_backward_assemble_kernel(Geom g, const float2 *__restrict__ part, int has_ne
 // launchers
 // ---------------------------------------------------------------------------------------------
 const int *g_last_work_count = nullptr;     // inspection hook (cmax_last_worklist_count)
-int g_last_work_bins = 0;
 
 struct FastArgs {
     const int *cell_start;
@@ -987,7 +986,6 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     int *worklist = reinterpret_cast<int *>(ws + L.worklist);
     int *work_count = reinterpret_cast<int *>(ws + L.work_count);
     g_last_work_count = work_count;
-    g_last_work_bins = 1;
     float *lut = reinterpret_cast<float *>(ws + L.lut);
     const size_t smem_bin = (size_t)g.NC * sizeof(int);
     const size_t smem_heap = (size_t)g.K * kKnnBlock * 8;
