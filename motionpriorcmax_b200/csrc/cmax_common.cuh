@@ -118,6 +118,13 @@ __device__ __forceinline__ void red_add_f32x2(float *p, float a, float b)
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+// Four adjacent floats in one L2 atomic request; `p` must be 16-byte aligned.
+__device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
 // Python-style float floor division, the arithmetic of torch's `//` on float tensors
 // (c10 div_floor_floating) used by focus.py:186-187.
 __device__ __forceinline__ float floordiv_f32(float a, float b)

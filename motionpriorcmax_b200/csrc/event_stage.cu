@@ -93,8 +93,12 @@ event_forward_kernel(const float *__restrict__ events, const float *__restrict__
             for (int row = 0; row < 2; ++row) {
                 const int i0 = c.idx[row], i1 = c.idx[row + 2];
                 float *p0 = raw + base + i0;
-                if (i0 >= 0 && i1 >= 0 && (((base + i0) & 1) == 0)) {
+                const int off = (int)((base + i0) & 3);
+                if (i0 >= 0 && i1 >= 0 && (off & 1) == 0) {
                     red_add_f32x2(p0, v[row], v[row + 2]);
+                } else if (i0 >= 0 && i1 >= 0 && off == 1) {
+                    // (x1, x1+1) sit in the middle of an aligned quad: one 16-byte request
+                    red_add_f32x4(p0 - 1, 0.0f, v[row], v[row + 2], 0.0f);
                 } else {
                     if (i0 >= 0) atomicAdd(p0, v[row]);
                     if (i1 >= 0) atomicAdd(raw + base + i1, v[row + 2]);
