@@ -144,11 +144,11 @@ bin_points_kernel(const float *__restrict__ traj, Geom g, int *__restrict__ cell
 struct Heap {                       // per-thread max-heap on (d, j), column `tid` of two smem arrays
     float *hd;
     int *hj;
-    int K, cnt;
+    int K, cnt, stride;
     float rootd;
     int rootj;
-    __device__ __forceinline__ float &D(int k) { return hd[k * kKnnBlock]; }
-    __device__ __forceinline__ int &J(int k) { return hj[k * kKnnBlock]; }
+    __device__ __forceinline__ float &D(int k) { return hd[k * stride]; }
+    __device__ __forceinline__ int &J(int k) { return hj[k * stride]; }
     __device__ __forceinline__ void sift_down(int i, int size, float d, int j)
     {
         while (true) {
@@ -595,7 +595,7 @@ knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__re
                 int *__restrict__ jcut, unsigned *__restrict__ tau_max,
                 unsigned *__restrict__ tile_max, const int *__restrict__ worklist,
                 const int *__restrict__ work_count, int fused, float *__restrict__ lut,
-                float *__restrict__ lut_copy)
+                float *__restrict__ lut_copy, int lanes)
 {
     extern __shared__ float heap_mem[];
     const int tid = threadIdx.x;
@@ -603,15 +603,23 @@ knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__re
     const int *items = worklist;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int tiles = tiles_x * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
-    for (int64_t w = (int64_t)blockIdx.x * kKnnBlock + tid; w < total; w += (int64_t)gridDim.x * kKnnBlock) {
+    // Work-list items are scattered, hard cells with very different ring counts: a warp runs the
+    // union of its lanes' paths, so only `lanes` (8) lanes per warp take an item - shorter serial
+    // chains per warp and 4x more warps in flight.  The dense all-query mode uses all 32 lanes.
+    const int lane = tid & 31, wid = tid >> 5;
+    const int per_cta = lanes * (kKnnBlock / 32);
+    const int col = wid * lanes + lane;                   // heap column of this thread
+    if (lane >= lanes) return;
+    for (int64_t w = (int64_t)blockIdx.x * per_cta + col; w < total; w += (int64_t)gridDim.x * per_cta) {
         const int64_t sq = bin < 0 ? w : (int64_t)items[w];
         const int64_t slab = sq / g.q;
         const Query q = make_query((int)(sq - slab * g.q), g);
         const int *cstart = cell_start + slab * (g.NC + 1);
         const float4 *sorted = sorted_all + slab * g.n;
         Heap h;
-        h.hd = heap_mem + tid;
-        h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * kKnnBlock) + tid;
+        h.stride = per_cta;
+        h.hd = heap_mem + col;
+        h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * per_cta) + col;
         h.K = g.K;
         h.cnt = 0;
         h.rootd = INFINITY;
@@ -706,6 +714,7 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
         const int r = radius_for(t_d, q.cqy, q.cqx, g, q.qy, q.qx);
         if (what & 4) {
             Heap h;
+            h.stride = kKnnBlock;
             h.hd = heap_mem + tid;
             h.hj = reinterpret_cast<int *>(heap_mem + (size_t)g.K * kKnnBlock) + tid;
             h.K = g.K;
@@ -1032,15 +1041,15 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
                 else launch_fast<false, false>(g, bin, grid, st, a);
             }
         }
-        knn_heap_kernel<<<148 * 4, kKnnBlock, smem_heap, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
-                                                             tau_max, tile_max, worklist, work_count,
-                                                             fused ? 1 : 0, lut, lc);
+        knn_heap_kernel<<<148 * 16, kKnnBlock, smem_heap / 4, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
+                                                                  tau_max, tile_max, worklist, work_count,
+                                                                  fused ? 1 : 0, lut, lc, 8);
         count_launch((per_bin ? g.nb : 1) + 1);
     } else {
         cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
         knn_heap_kernel<<<148 * 8, kKnnBlock, smem_heap, st>>>(traj, g, -1, cell_start, sorted, tau, jcut,
                                                              tau_max, tile_max, worklist, work_count,
-                                                             fused ? 1 : 0, lut, lc);
+                                                             fused ? 1 : 0, lut, lc, 32);
         count_launch();
     }
     const int acc_grid = 148 * 16;
