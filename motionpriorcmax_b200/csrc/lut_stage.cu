@@ -801,7 +801,7 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
 // stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
 // fixed order -> deterministic, and 15x more threads in flight for the latency-bound gather.
 template <bool L1D, bool IWD, bool F2N, int RT>   // RT = compile-time R (1) or 0 = runtime R
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64, 24)
 lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restrict__ tau,
                     const int *__restrict__ jcut, const float *__restrict__ wsum,
                     const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
