@@ -96,6 +96,42 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
                   const float *grad_loss, float *dtraj_out,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- packed, tile-binned event layout (the loader-side layout of SURVEY.md 8f rank 2) ----------
+ * Replaces the `batch['events']` tensor the reference collate builds (src/loader/dsec/loader.py
+ * :141-182,360-415) by 16-byte records without padding rows, grouped so that the event kernels can
+ * accumulate in shared memory:
+ *   records   [B, M, 4] float32: (y, x, t, meta), meta = the bit pattern of
+ *             bin << 24 | iy << 12 | ix, the event's LUT cell (upstream focus.py:185-187:
+ *             it = int(bin), iy = int(y // s), ix = int(x // s)); only rows with valid != 0 whose
+ *             cell lies inside the table are kept (valid is treated as 1);
+ *   seg_start [B, G * NT + 1] int32: per sample, prefix offsets of the segments ordered by
+ *             (polarity group g < G, source tile T < NT); G = 2 when polarity aware, else 1;
+ *             tile T = (iy / ct) * tiles_x + ix / ct; the last entry is the number of records.
+ * The order of the records inside a segment is free.
+ * cmax_pack_layout: host query, out = {ct (LUT cells per tile edge), tiles_y, tiles_x, G}.
+ * cmax_pack_events: builds the layout on the device from an upstream-layout events tensor;
+ *   scratch [B, G * NT] int32; skipped_out (optional) int64[2] DEVICE counters:
+ *   [0] valid rows dropped because their LUT cell is outside the table (cmax_forward counts the
+ *   same rows in its status word), [1] rows whose `valid` is neither 0 nor 1.
+ * Limits: num_bins <= 256, H/s and W/s <= 4096 (else CMAX_ERR_UNSUPPORTED). */
+int cmax_pack_layout(const CmaxConfig *cfg, int32_t out_host[4]);
+int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int64_t M,
+                     int64_t num_pos_events, float *records_out, int32_t *seg_start_out,
+                     int32_t *scratch, int64_t *skipped_out, void *stream);
+
+/* cmax_forward / cmax_backward on the packed layout: same outputs, same workspace
+ * (cmax_workspace_bytes(cfg, B, M, n) with the M of `records`).  The event stage accumulates
+ * the IWE votes of a (tile, group) segment in a shared-memory window and flushes once; votes
+ * leaving the window fall back to global atomics, so the result is exact for any flow. */
+int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                        const float *records, const int32_t *seg_start, int64_t B, int64_t M,
+                        int64_t n, float *iwes_out, float *losses_out, float *flow_lut_out,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                         const float *records, const int32_t *seg_start, int64_t B, int64_t M,
+                         int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
 /* Stand-alone imager, upstream EventImageConverter.create_iwe(events, method='bilinear_vote',
  * sigma, weight) (src/utils/event_image_converter.py:45-74,134-176,333-391).
  *   events [nb, M, row_stride] (first two columns y, x; row_stride >= 2 floats)

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(OUT_DIR, "libcmax_b200.so")
-SOURCES = ["api.cu", "lut_stage.cu", "event_stage.cu", "image_stage.cu", "voxel_stage.cu", "flow_stage.cu"]
+SOURCES = ["api.cu", "lut_stage.cu", "event_stage.cu", "tile_stage.cu", "image_stage.cu", "voxel_stage.cu", "flow_stage.cu"]
 HEADERS = [os.path.join(CSRC, "cmax_common.cuh"),
            os.path.join(os.path.dirname(PKG), "include", "cmax_b200.h")]
 NVCC_FLAGS = [

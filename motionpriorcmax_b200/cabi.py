@@ -24,6 +24,7 @@ EXPORTS = (
     "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
     "cmax_last_worklist_count", "cmax_voxel_grid", "cmax_dense_flow",
+    "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
 )
 
 
@@ -63,6 +64,16 @@ def load():
     lib.cmax_backward.restype = c_int32
     lib.cmax_backward.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, c_int64, c_int64,
                                   P, P, P, c_size_t, P]
+    lib.cmax_pack_layout.restype = c_int32
+    lib.cmax_pack_layout.argtypes = [POINTER(CmaxConfig), POINTER(c_int32 * 4)]
+    lib.cmax_pack_events.restype = c_int32
+    lib.cmax_pack_events.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, P, P, P, P]
+    lib.cmax_forward_packed.restype = c_int32
+    lib.cmax_forward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
+                                        P, P, P, P, c_size_t, P]
+    lib.cmax_backward_packed.restype = c_int32
+    lib.cmax_backward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
+                                         P, P, P, c_size_t, P]
     lib.cmax_create_iwe.restype = c_int32
     lib.cmax_create_iwe.argtypes = [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_float, P,
                                     P, P, c_int32, P]
@@ -135,6 +146,13 @@ def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_sup
         raise ValueError(f"focus_loss_type={focus_loss_type!r} not in {sorted(FOCUS)}")
     c.focus_functional = FOCUS[focus_loss_type]
     return c
+
+
+def pack_layout(cfg: CmaxConfig):
+    """(ct, tiles_y, tiles_x, G) of the packed event layout for this configuration."""
+    out = (c_int32 * 4)()
+    check(load().cmax_pack_layout(cfg, ctypes.byref(out)), "cmax_pack_layout")
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
 
 def stage_timing_read():

@@ -8,7 +8,6 @@ namespace cmax {
 
 int launch_splat(int mode, const float *events, const float *weight, int64_t nb, int64_t M,
                  int64_t stride, int H, int W, float *out, long long *out_i64, cudaStream_t st);
-int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStream_t st);
 int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
                 cudaStream_t st);
 extern const int *g_last_work_count;
@@ -19,7 +18,7 @@ extern const int *g_last_work_count;
 static const char *kStageNames[ST_COUNT] = {
     "bin_points", "knn_select", "event_forward", "image_forward", "smooth_forward", "finalize",
     "image_backward", "smooth_backward", "event_backward", "lut_backward", "traj_forward",
-    "traj_backward"};
+    "traj_backward", "pack_events"};
 constexpr int kMaxTimed = 8192;
 static bool g_timing = false;
 static cudaEvent_t g_ev[kMaxTimed][2];
@@ -127,6 +126,11 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     g->M = M;
     g->S = B * c->num_bins;
     g->npos = npos;
+    // packed (tile-binned) event layout: source tiles of ct x ct LUT cells, ~32 px on a side
+    g->ct = 32 / g->s > 0 ? 32 / g->s : 1;
+    g->nty = (g->Hq + g->ct - 1) / g->ct;
+    g->ntx = (g->Wq + g->ct - 1) / g->ct;
+    g->nt = g->nty * g->ntx;
     return CMAX_OK;
 }
 
@@ -396,6 +400,89 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
     if ((rc = launch_image_backward(g, L, ws, st))) return rc;
     if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
     if ((rc = launch_event_backward(g, L, events, times, grad_loss, ws, st))) return rc;
+    return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
+}
+
+static int pack_supported(const Geom &g)
+{
+    if (g.nb > 256 || g.Hq > 4096 || g.Wq > 4096 || g.M > (int64_t)INT32_MAX) return CMAX_ERR_UNSUPPORTED;
+    return CMAX_OK;
+}
+
+int cmax_pack_layout(const CmaxConfig *cfg, int32_t out_host[4])
+{
+    Geom g;
+    int rc = make_geom(cfg, 1, 0, cfg ? cfg->num_knn : 1, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!out_host) return CMAX_ERR_BAD_SHAPE;
+    if ((rc = pack_supported(g))) return rc;
+    out_host[0] = g.ct;
+    out_host[1] = g.nty;
+    out_host[2] = g.ntx;
+    out_host[3] = g.P;
+    return CMAX_OK;
+}
+
+int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int64_t M,
+                     int64_t num_pos_events, float *records_out, int32_t *seg_start_out,
+                     int32_t *scratch, int64_t *skipped_out, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, cfg ? cfg->num_knn : 1, num_pos_events, &g);
+    if (rc != CMAX_OK) return rc;
+    if ((rc = pack_supported(g))) return rc;
+    if ((!events && M > 0) || (!records_out && M > 0) || !seg_start_out || !scratch) return CMAX_ERR_BAD_SHAPE;
+    if (((uintptr_t)records_out & 15u)) return CMAX_ERR_WORKSPACE;
+    return launch_pack_events(g, events, reinterpret_cast<float4 *>(records_out), seg_start_out, scratch,
+                              reinterpret_cast<long long *>(skipped_out), static_cast<cudaStream_t>(stream));
+}
+
+int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                        const float *records, const int32_t *seg_start, int64_t B, int64_t M,
+                        int64_t n, float *iwes_out, float *losses_out, float *flow_lut_out,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if ((rc = pack_supported(g))) return rc;
+    if (!trajectories || !times || (!records && M > 0) || !seg_start || !iwes_out || !losses_out)
+        return CMAX_ERR_BAD_SHAPE;
+    if (((uintptr_t)records & 15u)) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(ws + L.header, 0, 1024, st);
+    if ((rc = launch_lut_forward(g, L, trajectories, ws, flow_lut_out, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_event_forward_packed(g, L, reinterpret_cast<const float4 *>(records), seg_start,
+                                          times, ws, st))) return rc;
+    if ((rc = launch_image_forward(g, L, ws, iwes_out, st))) return rc;
+    if ((rc = launch_smooth_forward(g, L, ws, st))) return rc;
+    return launch_finalize_losses(g, L, ws, losses_out, st);
+}
+
+int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                         const float *records, const int32_t *seg_start, int64_t B, int64_t M,
+                         int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
+                         size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if ((rc = pack_supported(g))) return rc;
+    if (!trajectories || !times || (!records && M > 0) || !seg_start || !grad_loss || !dtraj_out)
+        return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_image_backward(g, L, ws, st))) return rc;
+    if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
+    if ((rc = launch_event_backward_packed(g, L, reinterpret_cast<const float4 *>(records), seg_start,
+                                           times, grad_loss, ws, st))) return rc;
     return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
 }
 

@@ -39,6 +39,7 @@ struct Geom {                 // derived sizes, passed by value to kernels
     float smooth_w;
     int64_t B, M, n, S;       // S = B * nb
     int64_t npos;
+    int ct, nty, ntx, nt;     // packed event layout: source tiles of ct x ct LUT cells (tile_stage.cu)
 };
 
 struct Header {               // first 1 KiB of the workspace
@@ -71,6 +72,16 @@ int launch_event_forward(const Geom &g, const Layout &L, const float *events, co
                          char *ws, cudaStream_t st);
 int launch_event_backward(const Geom &g, const Layout &L, const float *events, const float *times,
                           const float *grad_loss, char *ws, cudaStream_t st);
+int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
+                       int *scratch, long long *skipped, cudaStream_t st);
+int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
+                                const int *seg_start, const float *times, char *ws, cudaStream_t st);
+int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *records,
+                                 const int *seg_start, const float *times, const float *grad_loss,
+                                 char *ws, cudaStream_t st);
+int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStream_t st);
+int launch_dlut_finalize(const Geom &g, const Layout &L, const float *grad_loss, char *ws,
+                         cudaStream_t st);
 int launch_image_forward(const Geom &g, const Layout &L, char *ws, float *iwes_out, cudaStream_t st);
 int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
 int launch_smooth_forward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
@@ -84,7 +95,7 @@ inline int check_launch() { return cudaGetLastError() == cudaSuccess ? CMAX_OK :
 // ---- optional per-stage timing (cudaEvent pairs on the launching stream) and launch counter ----
 enum Stage {
     ST_BIN_POINTS = 0, ST_KNN_SELECT, ST_EVENT_FWD, ST_IMAGE_FWD, ST_SMOOTH_FWD, ST_FINALIZE,
-    ST_IMAGE_BWD, ST_SMOOTH_BWD, ST_EVENT_BWD, ST_LUT_BWD, ST_TRAJ_FWD, ST_TRAJ_BWD, ST_COUNT
+    ST_IMAGE_BWD, ST_SMOOTH_BWD, ST_EVENT_BWD, ST_LUT_BWD, ST_TRAJ_FWD, ST_TRAJ_BWD, ST_PACK, ST_COUNT
 };
 void stage_begin(int stage, cudaStream_t st);
 void stage_end(int stage, cudaStream_t st);
@@ -180,6 +191,44 @@ __device__ __forceinline__ Corners vote_corners(float wy, float wx, int H, int W
     c.idx[2] = (y0ok && x1ok) ? iy * W + ix + 1 : -1;         // (y1,   x1+1)
     c.idx[3] = (y1ok && x1ok) ? (iy + 1) * W + ix + 1 : -1;   // (y1+1, x1+1)
     return c;
+}
+
+// ---- per-event helpers shared by event_stage.cu and tile_stage.cu ----
+struct EventRow { float y, x, t, p, bin, valid; };
+
+__device__ __forceinline__ EventRow load_event(const float *row)
+{
+    float2 a = ld_stream_f2(row), b = ld_stream_f2(row + 2), c = ld_stream_f2(row + 4);
+    EventRow e{a.x, a.y, b.x, b.y, c.x, c.y};
+    return e;
+}
+
+// LUT cell of an event (focus.py:185-187). Returns false when outside the table.
+__device__ __forceinline__ bool lut_cell(const EventRow &e, const Geom &g, int64_t b, int64_t *cell)
+{
+    float fs = (float)g.s;
+    float fy = floordiv_f32(e.y, fs), fx = floordiv_f32(e.x, fs);
+    float ft = truncf(e.bin);
+    if (!(ft >= 0.0f && ft < (float)g.nb && fy >= 0.0f && fy < (float)g.Hq && fx >= 0.0f &&
+          fx < (float)g.Wq))
+        return false;
+    *cell = ((b * g.nb + (int)ft) * g.Hq + (int)fy) * g.Wq + (int)fx;
+    return true;
+}
+
+// weight of a warped event (focus.py:201-214), no gradient flows through it
+__device__ __forceinline__ float event_weight(const EventRow &e, float wy, float wx, float tref,
+                                              const Geom &g)
+{
+    float w = e.valid;
+    if (g.scale_dt) {
+        float dt = fminf(fmaxf(fabsf(__fsub_rn(e.t, tref)), 0.0f), 1.0f);
+        w = __fmul_rn(__fsub_rn(1.0f, dt), w);
+    }
+    if (g.mask_border) {
+        if (wy > (float)g.H || wx > (float)g.W || wy < 0.0f || wx < 0.0f) w = 0.0f;
+    }
+    return w;
 }
 
 __device__ __forceinline__ double warp_sum(double v)

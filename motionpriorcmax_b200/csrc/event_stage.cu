@@ -12,43 +12,6 @@
 
 namespace cmax {
 
-struct EventRow { float y, x, t, p, bin, valid; };
-
-__device__ __forceinline__ EventRow load_event(const float *row)
-{
-    float2 a = ld_stream_f2(row), b = ld_stream_f2(row + 2), c = ld_stream_f2(row + 4);
-    EventRow e{a.x, a.y, b.x, b.y, c.x, c.y};
-    return e;
-}
-
-// LUT cell of an event (focus.py:185-187). Returns false when outside the table.
-__device__ __forceinline__ bool lut_cell(const EventRow &e, const Geom &g, int64_t b, int64_t *cell)
-{
-    float fs = (float)g.s;
-    float fy = floordiv_f32(e.y, fs), fx = floordiv_f32(e.x, fs);
-    float ft = truncf(e.bin);
-    if (!(ft >= 0.0f && ft < (float)g.nb && fy >= 0.0f && fy < (float)g.Hq && fx >= 0.0f &&
-          fx < (float)g.Wq))
-        return false;
-    *cell = ((b * g.nb + (int)ft) * g.Hq + (int)fy) * g.Wq + (int)fx;
-    return true;
-}
-
-// weight of a warped event (focus.py:201-214), no gradient flows through it
-__device__ __forceinline__ float event_weight(const EventRow &e, float wy, float wx, float tref,
-                                              const Geom &g)
-{
-    float w = e.valid;
-    if (g.scale_dt) {
-        float dt = fminf(fmaxf(fabsf(__fsub_rn(e.t, tref)), 0.0f), 1.0f);
-        w = __fmul_rn(__fsub_rn(1.0f, dt), w);
-    }
-    if (g.mask_border) {
-        if (wy > (float)g.H || wx > (float)g.W || wy < 0.0f || wx < 0.0f) w = 0.0f;
-    }
-    return w;
-}
-
 template <bool DET>
 __global__ void __launch_bounds__(256)
 event_forward_kernel(const float *__restrict__ events, const float *__restrict__ times, Geom g,
@@ -288,11 +251,18 @@ int launch_event_backward(const Geom &g, const Layout &L, const float *events, c
             event_backward_kernel<false><<<grid, 256, 0, st>>>(events, times, g, lut, dimg, hdr,
                                                                 grad_loss, dlut, dlut_i64);
     }
-    if (g.det) {
-        const double N = (double)g.B * g.R * g.P * (double)g.H * g.W;
-        dlut_finalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dlut_i64, dlut, hdr,
-                                                                             grad_loss, N, count);
-    }
+    if (g.det) return launch_dlut_finalize(g, L, grad_loss, ws, st);
+    return check_launch();
+}
+
+int launch_dlut_finalize(const Geom &g, const Layout &L, const float *grad_loss, char *ws,
+                         cudaStream_t st)
+{
+    const int64_t count = g.S * g.q * g.R * 2;
+    const double N = (double)g.B * g.R * g.P * (double)g.H * g.W;
+    dlut_finalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const long long *>(ws + L.dlut_i64), reinterpret_cast<float *>(ws + L.dlut),
+        reinterpret_cast<const Header *>(ws + L.header), grad_loss, N, count);
     return check_launch();
 }
 

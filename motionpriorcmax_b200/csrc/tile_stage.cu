@@ -1,0 +1,581 @@
+// tile_stage.cu - the event stage on the PACKED, tile-binned event layout (the
+// north star's "bin events by spatial tile, accumulate privately in shared memory, flush once").
+//
+// Same arithmetic as event_stage.cu (upstream src/losses/focus.py:182-230 and
+// src/utils/event_image_converter.py:333-391), different data movement:
+//
+//   packed records  float4 [B, M]   (y, x, t, meta)  meta = bin << 24 | iy << 12 | ix, the event's
+//                                    LUT cell (focus.py:185-187) evaluated ONCE at pack time;
+//                                    only valid rows are kept (16 B instead of 24 B, no padding)
+//   seg_start       int32  [B, G*NT + 1]  records of a sample are grouped by polarity group g
+//                                    (G = 2 when polarity aware) and by SOURCE tile T of ct x ct
+//                                    LUT cells (~32 x 32 pixels); prefix offsets per sample.
+//
+// Events of one (tile, group) segment are warped by the flows of one small LUT block, so their
+// votes land in a compact neighbourhood of the tile.  One CTA per segment (slice):
+//   forward   votes go into a 64 x 64 pixel window in SHARED memory (red.shared.add.f32, or u64
+//             fixed point when deterministic) whose origin follows the flow range of the tile's
+//             LUT block; one flush of the non-zero quads with red.global.add.v4.f32.
+//             Votes that leave the window fall back to the global reds of event_stage.cu, so any
+//             flow magnitude stays exact.
+//   backward  the same window of dL/dIWE is staged in shared memory, the four gathers are
+//             shared-memory loads, and (g_y, g_x) is reduced per LUT cell of the tile in shared
+//             memory before ONE red.global.add.v2.f32 per touched cell.
+// The binning itself does not depend on the flow: it is done once per window by the loader
+// (motionpriorcmax_b200.io.pack_events_host) or on the device (pack_* kernels below).
+#include <type_traits>
+
+#include "cmax_common.cuh"
+
+namespace cmax {
+
+constexpr int kWin = 64;                 // shared-memory window edge in pixels
+constexpr int kTileThreads = 256;
+constexpr int kMaxSmemAcc = 96 * 1024;   // dLUT block accumulated in shared memory up to this size
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side packing: count -> scan -> scatter
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pack_key(const EventRow &e, const Geom &g, int64_t m, int *key,
+                                         unsigned *meta)
+{
+    int64_t cell;
+    if (!lut_cell(e, g, 0, &cell)) return false;
+    const int bin = (int)(cell / g.q);
+    const int rem = (int)(cell - (int64_t)bin * g.q);
+    const int iy = rem / g.Wq, ix = rem - iy * g.Wq;
+    const int grp = (g.pab && m >= g.npos) ? 1 : 0;
+    *key = grp * g.nt + (iy / g.ct) * g.ntx + ix / g.ct;
+    *meta = ((unsigned)bin << 24) | ((unsigned)iy << 12) | (unsigned)ix;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+pack_count_kernel(const float *__restrict__ events, Geom g, int *__restrict__ counts,
+                  long long *__restrict__ skipped)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (m >= g.M) return;
+    const EventRow e = load_event(events + (b * g.M + m) * 6);
+    if (e.valid == 0.0f) return;
+    int key;
+    unsigned meta;
+    if (!pack_key(e, g, m, &key, &meta)) {
+        if (skipped) atomicAdd(reinterpret_cast<unsigned long long *>(skipped), 1ull);
+        return;
+    }
+    if (e.valid != 1.0f && skipped) atomicAdd(reinterpret_cast<unsigned long long *>(skipped + 1), 1ull);
+    atomicAdd(counts + b * (int64_t)(g.P * g.nt) + key, 1);
+}
+
+// one CTA per sample: exclusive scan of the G*NT counters -> seg_start, cursors
+__global__ void __launch_bounds__(1024)
+pack_scan_kernel(Geom g, int *__restrict__ counts, int *__restrict__ seg_start)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int n = g.P * g.nt;
+    const int64_t b = blockIdx.x;
+    int *cnt = counts + b * (int64_t)n;
+    int *out = seg_start + b * (int64_t)(n + 1);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_tot[lane], iw = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, iw, o);
+                if (lane >= o) iw += u;
+            }
+            warp_tot[lane] = iw - w;
+        }
+        __syncthreads();
+        const int excl = carry + warp_tot[wid] + incl - v;
+        if (i < n) {
+            out[i] = excl;
+            cnt[i] = excl;                               // cursor for the scatter
+        }
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+pack_scatter_kernel(const float *__restrict__ events, Geom g, int *__restrict__ cursor,
+                    float4 *__restrict__ records)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (m >= g.M) return;
+    const EventRow e = load_event(events + (b * g.M + m) * 6);
+    if (e.valid == 0.0f) return;
+    int key;
+    unsigned meta;
+    if (!pack_key(e, g, m, &key, &meta)) return;
+    const int pos = atomicAdd(cursor + b * (int64_t)(g.P * g.nt) + key, 1);
+    records[b * g.M + pos] = make_float4(e.y, e.x, e.t, __uint_as_float(meta));
+}
+
+int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
+                       int *scratch, long long *skipped, cudaStream_t st)
+{
+    StageScope sc(ST_PACK, st);
+    const int n = g.P * g.nt;
+    cudaMemsetAsync(scratch, 0, sizeof(int) * g.B * n, st);
+    if (skipped) cudaMemsetAsync(skipped, 0, sizeof(long long) * 2, st);
+    dim3 grid((unsigned)((g.M + 255) / 256), (unsigned)g.B);
+    count_launch(g.M > 0 ? 3 : 1);
+    if (g.M > 0) pack_count_kernel<<<grid, 256, 0, st>>>(events, g, scratch, skipped);
+    pack_scan_kernel<<<(unsigned)g.B, 1024, 0, st>>>(g, scratch, seg_start);
+    if (g.M > 0) pack_scatter_kernel<<<grid, 256, 0, st>>>(events, g, scratch, records);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared pieces of the tile kernels
+// ---------------------------------------------------------------------------------------------
+struct Seg {
+    int a, e;          // record range of this CTA inside its sample
+    int ty, tx, grp;
+};
+
+__device__ __forceinline__ Seg cta_segment(const Geom &g, const int *__restrict__ seg_start, int split)
+{
+    Seg s;
+    const int tile = blockIdx.x / split, part = blockIdx.x - tile * split;
+    s.grp = blockIdx.y;
+    s.ty = tile / g.ntx;
+    s.tx = tile - s.ty * g.ntx;
+    const int *row = seg_start + (int64_t)blockIdx.z * (g.P * g.nt + 1) + s.grp * g.nt + tile;
+    const int a = __ldg(row), e = __ldg(row + 1);
+    const int chunk = (e - a + split - 1) / split;
+    s.a = min(a + part * chunk, e);
+    s.e = min(s.a + chunk, e);
+    return s;
+}
+
+// Window origin for reference time r: the tile's pixel box grown by the range of the flows stored
+// in the tile's LUT block (all bins).  Only a placement heuristic - votes outside the window take
+// the global path - so forward and backward need not agree and NaN / huge flows are harmless.
+__device__ __forceinline__ void window_origin(const Geom &g, const float *__restrict__ lut, int64_t b,
+                                              const Seg &s, int r, float *s_red, int *oy, int *ox)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mny = INFINITY, mxy = -INFINITY, mnx = INFINITY, mxx = -INFINITY;
+    const int cc = g.ct * g.ct, tot = cc * g.nb;
+    for (int i = tid; i < tot; i += kTileThreads) {
+        const int bin = i / cc, c = i - bin * cc;
+        const int iy = s.ty * g.ct + c / g.ct, ix = s.tx * g.ct + c % g.ct;
+        if (iy < g.Hq && ix < g.Wq) {
+            const int64_t cell = ((b * g.nb + bin) * g.Hq + iy) * g.Wq + ix;
+            const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
+            mny = fminf(mny, f.x); mxy = fmaxf(mxy, f.x);
+            mnx = fminf(mnx, f.y); mxx = fmaxf(mxx, f.y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    }
+    if (lane == 0) {
+        s_red[wid * 4 + 0] = mny; s_red[wid * 4 + 1] = mxy;
+        s_red[wid * 4 + 2] = mnx; s_red[wid * 4 + 3] = mxx;
+    }
+    __syncthreads();
+    for (int w = 0; w < kTileThreads / 32; ++w) {
+        mny = fminf(mny, s_red[w * 4 + 0]); mxy = fmaxf(mxy, s_red[w * 4 + 1]);
+        mnx = fminf(mnx, s_red[w * 4 + 2]); mxx = fmaxf(mxx, s_red[w * 4 + 3]);
+    }
+    __syncthreads();
+    const int tp = g.ct * g.s;
+    auto place = [&](int t0, float mn, float mx) {
+        if (!(mn > -1e6f && mx < 1e6f)) return t0 - (kWin - tp) / 2;
+        const int lo = t0 + (int)floorf(mn) - 1, hi = t0 + tp + (int)ceilf(mx) + 2;
+        return hi - lo <= kWin ? lo : (lo + hi) / 2 - kWin / 2;
+    };
+    *oy = place(s.ty * tp, mny, mxy);
+    *ox = place(s.tx * tp, mnx, mxx) & ~3;          // quads of the flush stay 16-byte aligned
+}
+
+struct PackedEvent {
+    EventRow e;
+    int bin, iy, ix;
+};
+
+__device__ __forceinline__ PackedEvent unpack(const float4 rec)
+{
+    PackedEvent p;
+    const unsigned meta = __float_as_uint(rec.w);
+    p.bin = (int)(meta >> 24);
+    p.iy = (int)((meta >> 12) & 0xfffu);
+    p.ix = (int)(meta & 0xfffu);
+    p.e.y = rec.x; p.e.x = rec.y; p.e.t = rec.z;
+    p.e.p = 0.0f; p.e.bin = (float)p.bin; p.e.valid = 1.0f;
+    return p;
+}
+
+// corners with (row, column) kept separate, plus the per-corner in-image flags of
+// event_image_converter.py:362-377
+struct Corners2 {
+    int y, x;            // integer (y1, x1); only meaningful when `finite`
+    bool finite;         // y1, x1 within int range of the image neighbourhood
+    bool y0ok, y1ok, x0ok, x1ok;
+    float fy, fx;
+};
+
+__device__ __forceinline__ Corners2 vote_corners2(float wy, float wx, int H, int W)
+{
+    Corners2 c;
+    const float y1 = floorf(__fadd_rn(wy, kVoteEps));
+    const float x1 = floorf(__fadd_rn(wx, kVoteEps));
+    c.fy = __fsub_rn(wy, y1);
+    c.fx = __fsub_rn(wx, x1);
+    c.y0ok = (y1 >= 0.0f) && (y1 < (float)H);
+    c.y1ok = (y1 >= -1.0f) && (y1 < (float)(H - 1));
+    c.x0ok = (x1 >= 0.0f) && (x1 < (float)W);
+    c.x1ok = (x1 >= -1.0f) && (x1 < (float)(W - 1));
+    c.finite = (c.y0ok || c.y1ok) && (c.x0ok || c.x1ok);
+    c.y = c.finite ? (int)y1 : 0;
+    c.x = c.finite ? (int)x1 : 0;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <bool DET>
+__global__ void __launch_bounds__(kTileThreads)
+event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restrict__ seg_start,
+                          const float *__restrict__ times, Geom g, int split,
+                          const float *__restrict__ lut, float *__restrict__ raw,
+                          long long *__restrict__ raw_i64)
+{
+    using Acc = typename std::conditional<DET, unsigned long long, float>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Acc *s_win = reinterpret_cast<Acc *>(smem_raw);
+    __shared__ float s_red[4 * kTileThreads / 32];
+
+    const Seg sg = cta_segment(g, seg_start, split);
+    if (sg.a >= sg.e) return;
+    const int64_t b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int64_t HW = (int64_t)g.H * g.W;
+    const float4 *recs = records + b * g.M;
+    const bool use_win = sg.e - sg.a >= 64;              // tiny slices: global reds are cheaper
+
+    for (int r = 0; r < g.R; ++r) {
+        int oy = 0, ox = 0;
+        if (use_win) {
+            window_origin(g, lut, b, sg, r, s_red, &oy, &ox);
+            for (int i = tid; i < kWin * kWin; i += kTileThreads) s_win[i] = (Acc)0;
+            __syncthreads();
+        }
+        const float tref = __ldg(times + r);
+        const int64_t base = ((b * g.R + r) * g.P + sg.grp) * HW;
+        for (int i = sg.a + tid; i < sg.e; i += kTileThreads) {
+            const PackedEvent pe = unpack(ld_stream_f4(recs + i));
+            if (pe.bin >= g.nb || pe.iy >= g.Hq || pe.ix >= g.Wq) continue;      // corrupt record
+            const int64_t cell = ((b * g.nb + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
+            const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
+            const float wy = __fadd_rn(f.x, pe.e.y), wx = __fadd_rn(f.y, pe.e.x);     // focus.py:191
+            const float w = event_weight(pe.e, wy, wx, tref, g);
+            if (w == 0.0f) continue;
+            const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
+            if (!c.finite) continue;
+            const float oyw = __fsub_rn(1.0f, c.fy), oxw = __fsub_rn(1.0f, c.fx);
+            float v[4];
+            v[0] = __fmul_rn(__fmul_rn(oyw, oxw), w);        // event_image_converter.py:382-385
+            v[1] = __fmul_rn(__fmul_rn(c.fy, oxw), w);
+            v[2] = __fmul_rn(__fmul_rn(oyw, c.fx), w);
+            v[3] = __fmul_rn(__fmul_rn(c.fy, c.fx), w);
+            const bool ok[4] = {c.y0ok && c.x0ok, c.y1ok && c.x0ok, c.y0ok && c.x1ok, c.y1ok && c.x1ok};
+            const int ly = c.y - oy, lx = c.x - ox;
+            if (use_win && ly >= 0 && ly < kWin - 1 && lx >= 0 && lx < kWin - 1) {
+                Acc *p = s_win + ly * kWin + lx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!ok[k]) continue;
+                    Acc *q = p + (k & 1) * kWin + (k >> 1);
+                    if (DET)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(q),
+                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                    else
+                        atomicAdd(reinterpret_cast<float *>(q), v[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!ok[k]) continue;
+                    const int64_t idx = base + (int64_t)(c.y + (k & 1)) * g.W + c.x + (k >> 1);
+                    if (DET)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + idx),
+                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                    else
+                        atomicAdd(raw + idx, v[k]);
+                }
+            }
+        }
+        if (!use_win) continue;
+        __syncthreads();
+        // flush the non-zero part of the window
+        if (DET) {
+            for (int i = tid; i < kWin * kWin; i += kTileThreads) {
+                const unsigned long long v = reinterpret_cast<unsigned long long *>(s_win)[i];
+                const int gy = oy + i / kWin, gx = ox + i % kWin;
+                if (v != 0ull && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + (int64_t)gy * g.W + gx), v);
+            }
+        } else {
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_win);
+            for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
+                const float4 v = w4[i];
+                if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
+                const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));
+                if (gy < 0 || gy >= g.H) continue;
+                const int64_t idx = base + (int64_t)gy * g.W + gx;
+                if (gx >= 0 && gx + 3 < g.W && (idx & 3) == 0) {
+                    red_add_f32x4(raw + idx, v.x, v.y, v.z, v.w);
+                } else {
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (vv[k] != 0.0f && gx + k >= 0 && gx + k < g.W) atomicAdd(raw + idx + k, vv[k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <bool DET>
+__global__ void __launch_bounds__(kTileThreads)
+event_backward_tile_kernel(const float4 *__restrict__ records, const int *__restrict__ seg_start,
+                           const float *__restrict__ times, Geom g, int split, int smem_acc,
+                           const float *__restrict__ lut, const float *__restrict__ dimg,
+                           const Header *__restrict__ hdr, const float *__restrict__ grad_loss,
+                           float *__restrict__ dlut, long long *__restrict__ dlut_i64)
+{
+    using Acc = typename std::conditional<DET, unsigned long long, float>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_D = reinterpret_cast<float *>(smem_raw);                       // [kWin * kWin]
+    Acc *s_acc = reinterpret_cast<Acc *>(smem_raw + sizeof(float) * kWin * kWin);   // [nb, ct, ct, 2]
+    __shared__ float s_red[4 * kTileThreads / 32];
+
+    const Seg sg = cta_segment(g, seg_start, split);
+    if (sg.a >= sg.e) return;
+    const int64_t b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int64_t HW = (int64_t)g.H * g.W;
+    const float4 *recs = records + b * g.M;
+    const bool use_win = sg.e - sg.a >= 64;
+    const bool use_acc = use_win && smem_acc;
+    const int cc = g.ct * g.ct, nacc = cc * g.nb;
+    float coef = 1.0f;
+    if (!DET) {
+        const float val = hdr->val;
+        const float N = (float)((double)g.B * g.R * g.P * (double)HW);
+        coef = __ldg(grad_loss) * (-(1.0f / (val * val))) / N;
+    }
+
+    for (int r = 0; r < g.R; ++r) {
+        const float *D = dimg + ((b * g.R + r) * g.P + sg.grp) * HW;
+        int oy = 0, ox = 0;
+        if (use_win) {
+            window_origin(g, lut, b, sg, r, s_red, &oy, &ox);
+            for (int i = tid; i < kWin * kWin; i += kTileThreads) {
+                const int gy = oy + i / kWin, gx = ox + i % kWin;
+                s_D[i] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? __ldg(D + (int64_t)gy * g.W + gx) : 0.0f;
+            }
+            if (use_acc)
+                for (int i = tid; i < nacc * 2; i += kTileThreads) s_acc[i] = (Acc)0;
+            __syncthreads();
+        }
+        const float tref = __ldg(times + r);
+        for (int i = sg.a + tid; i < sg.e; i += kTileThreads) {
+            const PackedEvent pe = unpack(ld_stream_f4(recs + i));
+            if (pe.bin >= g.nb || pe.iy >= g.Hq || pe.ix >= g.Wq) continue;      // corrupt record
+            const int64_t cell = ((b * g.nb + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
+            const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
+            const float wy = __fadd_rn(f.x, pe.e.y), wx = __fadd_rn(f.y, pe.e.x);
+            const float w = event_weight(pe.e, wy, wx, tref, g);
+            if (w == 0.0f) continue;
+            const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
+            if (!c.finite) continue;
+            float d00, d10, d01, d11;
+            const int ly = c.y - oy, lx = c.x - ox;
+            if (use_win && ly >= 0 && ly < kWin - 1 && lx >= 0 && lx < kWin - 1) {
+                const float *p = s_D + ly * kWin + lx;      // zero outside the image
+                d00 = (c.y0ok && c.x0ok) ? p[0] : 0.0f;
+                d10 = (c.y1ok && c.x0ok) ? p[kWin] : 0.0f;
+                d01 = (c.y0ok && c.x1ok) ? p[1] : 0.0f;
+                d11 = (c.y1ok && c.x1ok) ? p[kWin + 1] : 0.0f;
+            } else {
+                const float *p = D + (int64_t)c.y * g.W + c.x;
+                d00 = (c.y0ok && c.x0ok) ? __ldg(p) : 0.0f;
+                d10 = (c.y1ok && c.x0ok) ? __ldg(p + g.W) : 0.0f;
+                d01 = (c.y0ok && c.x1ok) ? __ldg(p + 1) : 0.0f;
+                d11 = (c.y1ok && c.x1ok) ? __ldg(p + g.W + 1) : 0.0f;
+            }
+            const float oyw = 1.0f - c.fy, oxw = 1.0f - c.fx;
+            const float gy = w * (oxw * (d10 - d00) + c.fx * (d11 - d01));
+            const float gx = w * (oyw * (d01 - d00) + c.fy * (d11 - d10));
+            const int cy = pe.iy - sg.ty * g.ct, cx = pe.ix - sg.tx * g.ct;
+            if (use_acc && (unsigned)cy < (unsigned)g.ct && (unsigned)cx < (unsigned)g.ct) {
+                Acc *q = s_acc + 2 * ((pe.bin * g.ct + cy) * g.ct + cx);
+                if (DET) {
+                    atomicAdd(reinterpret_cast<unsigned long long *>(q),
+                              (unsigned long long)__double2ll_rn((double)gy * kFixScale));
+                    atomicAdd(reinterpret_cast<unsigned long long *>(q) + 1,
+                              (unsigned long long)__double2ll_rn((double)gx * kFixScale));
+                } else {
+                    atomicAdd(reinterpret_cast<float *>(q), coef * gy);
+                    atomicAdd(reinterpret_cast<float *>(q) + 1, coef * gx);
+                }
+            } else if (DET) {
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
+                atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
+                atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
+            } else {
+                red_add_f32x2(dlut + (cell * g.R + r) * 2, coef * gy, coef * gx);
+            }
+        }
+        if (!use_win) continue;
+        __syncthreads();
+        if (use_acc) {
+            for (int i = tid; i < nacc; i += kTileThreads) {
+                const int bin = i / cc, c2 = i - bin * cc;
+                const int iy = sg.ty * g.ct + c2 / g.ct, ix = sg.tx * g.ct + c2 % g.ct;
+                if (iy >= g.Hq || ix >= g.Wq) continue;
+                const int64_t cell = ((b * g.nb + bin) * g.Hq + iy) * g.Wq + ix;
+                if (DET) {
+                    const unsigned long long a0 = reinterpret_cast<unsigned long long *>(s_acc)[2 * i];
+                    const unsigned long long a1 = reinterpret_cast<unsigned long long *>(s_acc)[2 * i + 1];
+                    unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
+                    if (a0 != 0ull) atomicAdd(dst, a0);
+                    if (a1 != 0ull) atomicAdd(dst + 1, a1);
+                } else {
+                    const float a0 = reinterpret_cast<float *>(s_acc)[2 * i];
+                    const float a1 = reinterpret_cast<float *>(s_acc)[2 * i + 1];
+                    if (a0 != 0.0f || a1 != 0.0f) red_add_f32x2(dlut + (cell * g.R + r) * 2, a0, a1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int pick_split(const Geom &g)
+{
+    // slices of ~8k events: enough CTAs for every SM when a window holds tens of millions of events
+    const int64_t per_seg = g.M / ((int64_t)g.P * g.nt) + 1;
+    int64_t s = (per_seg + 8191) / 8192;
+    return (int)(s < 1 ? 1 : (s > 32 ? 32 : s));
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return CMAX_ERR_CUDA;
+    return CMAX_OK;
+}
+
+int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
+                                const int *seg_start, const float *times, char *ws, cudaStream_t st)
+{
+    const int64_t count = g.B * g.R * g.P * (int64_t)g.H * g.W;
+    float *raw = reinterpret_cast<float *>(ws + L.raw);
+    long long *raw_i64 = reinterpret_cast<long long *>(ws + L.raw_i64);
+    const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    StageScope sc(ST_EVENT_FWD, st);
+    count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
+    if (g.det)
+        cudaMemsetAsync(raw_i64, 0, sizeof(long long) * count, st);
+    else
+        cudaMemsetAsync(raw, 0, sizeof(float) * count, st);
+    if (g.M > 0) {
+        const int split = pick_split(g);
+        dim3 grid((unsigned)(g.nt * split), (unsigned)g.P, (unsigned)g.B);
+        if (g.det) {
+            const size_t sm = sizeof(unsigned long long) * kWin * kWin;
+            event_forward_tile_kernel<true><<<grid, kTileThreads, sm, st>>>(records, seg_start, times, g,
+                                                                            split, lut, raw, raw_i64);
+        } else {
+            const size_t sm = sizeof(float) * kWin * kWin;
+            event_forward_tile_kernel<false><<<grid, kTileThreads, sm, st>>>(records, seg_start, times, g,
+                                                                             split, lut, raw, raw_i64);
+        }
+    }
+    if (g.det) return launch_fix_to_float(raw_i64, raw, count, st);
+    return check_launch();
+}
+
+int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *records,
+                                 const int *seg_start, const float *times, const float *grad_loss,
+                                 char *ws, cudaStream_t st)
+{
+    const int64_t count = g.S * g.q * g.R * 2;
+    const Header *hdr = reinterpret_cast<const Header *>(ws + L.header);
+    const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    const float *dimg = reinterpret_cast<const float *>(ws + L.dimg);
+    float *dlut = reinterpret_cast<float *>(ws + L.dlut);
+    long long *dlut_i64 = reinterpret_cast<long long *>(ws + L.dlut_i64);
+    StageScope sc(ST_EVENT_BWD, st);
+    count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
+    if (g.det) cudaMemsetAsync(dlut_i64, 0, sizeof(long long) * count, st);
+    if (g.M > 0) {
+        const int split = pick_split(g);
+        dim3 grid((unsigned)(g.nt * split), (unsigned)g.P, (unsigned)g.B);
+        const size_t acc = (size_t)g.ct * g.ct * g.nb * 2 * (g.det ? sizeof(unsigned long long) : sizeof(float));
+        const int smem_acc = acc <= (size_t)kMaxSmemAcc ? 1 : 0;
+        const size_t sm = sizeof(float) * kWin * kWin + (smem_acc ? acc : 0);
+        int rc;
+        if (g.det) {
+            if ((rc = set_smem(event_backward_tile_kernel<true>, sm))) return rc;
+            event_backward_tile_kernel<true><<<grid, kTileThreads, sm, st>>>(
+                records, seg_start, times, g, split, smem_acc, lut, dimg, hdr, grad_loss, dlut, dlut_i64);
+        } else {
+            if ((rc = set_smem(event_backward_tile_kernel<false>, sm))) return rc;
+            event_backward_tile_kernel<false><<<grid, kTileThreads, sm, st>>>(
+                records, seg_start, times, g, split, smem_acc, lut, dimg, hdr, grad_loss, dlut, dlut_i64);
+        }
+    }
+    if (g.det) return launch_dlut_finalize(g, L, grad_loss, ws, st);
+    return check_launch();
+}
+
+}  // namespace cmax

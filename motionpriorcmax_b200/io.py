@@ -6,9 +6,16 @@ all-zero rows up to the batch maximum, separately for the positive and the negat
 the loss; copying them over PCIe is pure waste.  `EventUploader` copies only the valid prefix of
 each group from pinned host memory (asynchronously, on a copy stream, double buffered) and keeps
 the rest of the device buffer zero, so the device tensor is bit-identical to a full copy.
+
+`PackedEvents` is the loader-side layout of SURVEY.md 8f rank 2 (include/cmax_b200.h, "packed,
+tile-binned event layout"): 16-byte records of the valid events only, grouped by polarity group
+and 32x32-pixel source tile, so the event kernels accumulate in shared memory.  Build it in the
+loader workers with `pack_events_host` (torch CPU ops, no GPU) or on the device with
+`pack_events` (C ABI `cmax_pack_events`); pass it as `batch['events']` to `FocusLoss.calc`.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
@@ -97,6 +104,188 @@ class EventUploader:
                 new_ext.append(keep)
             lens = new_ext
             self.extent[slot] = lens
+            self.bytes_last = nbytes
+            self.ready[slot].record(self.stream)
+        return buf, slot
+
+    def wait(self, slot: int, stream=None):
+        (stream or torch.cuda.current_stream(self.device)).wait_event(self.ready[slot])
+
+    def release(self, slot: int, stream=None):
+        self.free[slot].record(stream or torch.cuda.current_stream(self.device))
+
+
+# ------------------------------------------------------------------------------------------------
+# packed, tile-binned event layout
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PackedEvents:
+    """records [B, M, 4] float32 (y, x, t, meta bits), seg_start [B, G*NT+1] int32; see
+    include/cmax_b200.h.  `skipped` (optional) int64[2]: valid rows dropped because their LUT cell
+    is outside the table / rows whose `valid` is neither 0 nor 1."""
+    records: torch.Tensor
+    seg_start: torch.Tensor
+    skipped: Optional[torch.Tensor] = None
+
+    @property
+    def is_cuda(self):
+        return self.records.is_cuda
+
+    @property
+    def device(self):
+        return self.records.device
+
+    def num_events(self) -> torch.Tensor:
+        return self.seg_start[:, -1]
+
+    def to(self, device, non_blocking: bool = False):
+        return PackedEvents(self.records.to(device, non_blocking=non_blocking),
+                            self.seg_start.to(device, non_blocking=non_blocking),
+                            None if self.skipped is None else self.skipped.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return PackedEvents(self.records.pin_memory(), self.seg_start.pin_memory(),
+                            None if self.skipped is None else self.skipped.pin_memory())
+
+
+def _cfg_of(loss_or_cfg):
+    return getattr(loss_or_cfg, "_cfg", loss_or_cfg)
+
+
+def pack_events(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg) -> PackedEvents:
+    """Device-side packing (three kernels) of an upstream-layout `[B, M, 6]` CUDA events tensor."""
+    from . import cabi
+    lib = cabi.load()
+    cfg = _cfg_of(loss_or_cfg)
+    if not events.is_cuda:
+        raise RuntimeError("pack_events needs a CUDA tensor (use pack_events_host in loader workers)")
+    ev = events.detach().to(torch.float32).contiguous()
+    B, M, six = ev.shape
+    assert six == 6, "events must be [B, M, 6]"
+    _, nty, ntx, G = cabi.pack_layout(cfg)
+    n_seg = G * nty * ntx
+    rec = torch.empty((B, M, 4), dtype=torch.float32, device=ev.device)
+    seg = torch.empty((B, n_seg + 1), dtype=torch.int32, device=ev.device)
+    scratch = torch.empty((B, n_seg), dtype=torch.int32, device=ev.device)
+    skipped = torch.empty(2, dtype=torch.int64, device=ev.device)
+    npos = -1 if num_pos_events is None else int(num_pos_events)
+    if not cfg.polarity_aware_batching:
+        npos = 0
+    cabi.check(lib.cmax_pack_events(cfg, cabi.ptr(ev), B, M, npos, cabi.ptr(rec), cabi.ptr(seg),
+                                    cabi.ptr(scratch), cabi.ptr(skipped), cabi.stream_ptr(ev.device)),
+               "cmax_pack_events")
+    return PackedEvents(rec, seg, skipped)
+
+
+def pack_events_host(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
+                     layout=None) -> PackedEvents:
+    """The same layout built with torch CPU ops - for DataLoader workers / the collate function.
+    `layout` = (ct, tiles_y, tiles_x, G) avoids loading the CUDA library in a worker process; by
+    default it is asked from the library (`cabi.pack_layout`)."""
+    cfg = _cfg_of(loss_or_cfg)
+    if layout is None:
+        from . import cabi
+        layout = cabi.pack_layout(cfg)
+    ct, nty, ntx, G = layout
+    s, nb = cfg.lut_superpixel_size, cfg.num_bins
+    Hq = (cfg.height + s - 1) // s
+    Wq = (cfg.width + s - 1) // s
+    nt = nty * ntx
+    ev = events.detach().to(torch.float32).cpu()
+    B, M, _ = ev.shape
+    npos = int(num_pos_events) if (cfg.polarity_aware_batching and num_pos_events is not None) else None
+    if cfg.polarity_aware_batching and (npos is None or npos < 0 or npos > M):
+        raise ValueError("polarity-aware packing needs 0 <= num_pos_events <= M")
+    # focus.py:185-187 - the reference's own index arithmetic (float floor division, truncation)
+    it = ev[..., 4].to(torch.int64)
+    fy, fx = ev[..., 0] // s, ev[..., 1] // s
+    ok = (ev[..., 5] != 0) & (it >= 0) & (it < nb) & (fy >= 0) & (fy < Hq) & (fx >= 0) & (fx < Wq) \
+        & (ev[..., 4] == ev[..., 4])
+    dropped = int(((ev[..., 5] != 0) & ~ok).sum())
+    odd = int(((ev[..., 5] != 0) & (ev[..., 5] != 1)).sum())
+    iy = torch.where(ok, fy, torch.zeros_like(fy)).to(torch.int64)
+    ix = torch.where(ok, fx, torch.zeros_like(fx)).to(torch.int64)
+    it = torch.where(ok, it, torch.zeros_like(it))
+    grp = torch.zeros((B, M), dtype=torch.int64)
+    if npos is not None:
+        grp[:, npos:] = 1
+    key = grp * nt + (iy // ct) * ntx + ix // ct
+    key = torch.where(ok, key, torch.full_like(key, G * nt))          # dropped rows sort last
+    order = torch.argsort(key, dim=1, stable=True)
+    counts = torch.zeros((B, G * nt + 1), dtype=torch.int64)
+    counts.scatter_add_(1, key, torch.ones_like(key))
+    seg = torch.zeros((B, G * nt + 1), dtype=torch.int64)
+    seg[:, 1:] = torch.cumsum(counts[:, :G * nt], dim=1)
+    Mp = max(int(seg[:, -1].max()), 1)
+    meta = ((it << 24) | (iy << 12) | ix).to(torch.int32)
+    rec = torch.stack((ev[..., 0], ev[..., 1], ev[..., 2], meta.view(torch.float32)), dim=-1)
+    rec = torch.gather(rec, 1, order[:, :Mp, None].expand(B, Mp, 4)).contiguous()
+    return PackedEvents(rec, seg.to(torch.int32), torch.tensor([dropped, odd], dtype=torch.int64))
+
+
+def unpack_events(packed: PackedEvents, loss_or_cfg, layout=None) -> "tuple[torch.Tensor, Optional[int]]":
+    """Inverse for tests / debugging: an upstream-layout `[B, M', 6]` tensor (positives first,
+    zero padding, p = +1 / 0 by group) and `num_pos_events`, from a packed batch (CPU)."""
+    cfg = _cfg_of(loss_or_cfg)
+    if layout is None:
+        from . import cabi
+        layout = cabi.pack_layout(cfg)
+    _, nty, ntx, G = layout
+    nt = nty * ntx
+    rec, seg = packed.records.cpu(), packed.seg_start.cpu().to(torch.int64)
+    B = rec.shape[0]
+    meta = rec[..., 3].contiguous().view(torch.int32).to(torch.int64)
+    cnt = [[int(seg[b, (g + 1) * nt] - seg[b, g * nt]) for g in range(G)] for b in range(B)]
+    cap = [max(max(c[g] for c in cnt), 0) for g in range(G)]
+    out = torch.zeros((B, max(sum(cap), 1), 6), dtype=torch.float32)
+    for b in range(B):
+        off = 0
+        for g in range(G):
+            a, e = int(seg[b, g * nt]), int(seg[b, (g + 1) * nt])
+            rows = out[b, off:off + (e - a)]
+            rows[:, 0:3] = rec[b, a:e, 0:3]
+            rows[:, 3] = 1.0 if g == 0 else 0.0
+            rows[:, 4] = (meta[b, a:e] >> 24).to(torch.float32)
+            rows[:, 5] = 1.0
+            off += cap[g]
+    return out, (cap[0] if G == 2 else None)
+
+
+class PackedUploader:
+    """Double-buffered H2D staging of host-packed batches (pinned `PackedEvents`): per sample only
+    the `seg_start[b, -1]` records in use cross PCIe (16 B per valid event, no padding rows)."""
+
+    def __init__(self, device, n_buffers: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.n = n_buffers
+        self.bufs = [None] * n_buffers
+        self.ready = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.free = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.turn = 0
+        self.bytes_last = 0
+        for ev in self.free:
+            ev.record(torch.cuda.current_stream(self.device))
+
+    def upload(self, packed: PackedEvents, counts=None):
+        assert packed.records.is_pinned() and packed.seg_start.is_pinned()
+        slot = self.turn
+        self.turn = (self.turn + 1) % self.n
+        if counts is None:
+            counts = packed.seg_start[:, -1].tolist()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[slot])
+            buf = self.bufs[slot]
+            if buf is None or buf.records.shape != packed.records.shape:
+                buf = PackedEvents(torch.empty(packed.records.shape, dtype=torch.float32, device=self.device),
+                                   torch.empty(packed.seg_start.shape, dtype=torch.int32, device=self.device))
+                self.bufs[slot] = buf
+            nbytes = packed.seg_start.numel() * 4
+            buf.seg_start.copy_(packed.seg_start, non_blocking=True)
+            for b, c in enumerate(counts):
+                if c:
+                    buf.records[b, :c].copy_(packed.records[b, :c], non_blocking=True)
+                    nbytes += c * 16
             self.bytes_last = nbytes
             self.ready[slot].record(self.stream)
         return buf, slot

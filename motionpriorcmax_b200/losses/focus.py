@@ -20,7 +20,7 @@ class _CmaxLossFunction(torch.autograd.Function):
     """autograd node: forward = cmax_forward, backward = cmax_backward."""
 
     @staticmethod
-    def forward(ctx, trajectories, times, events, cfg, num_pos_events, want_lut):
+    def forward(ctx, trajectories, times, events, cfg, num_pos_events, want_lut, seg_start=None):
         lib = cabi.load()
         dev = trajectories.device
         traj = trajectories.detach().to(torch.float32).contiguous()
@@ -28,7 +28,15 @@ class _CmaxLossFunction(torch.autograd.Function):
         ev = events.detach().to(torch.float32).contiguous()
         B, n_t, n, two = traj.shape
         assert two == 2 and n_t == cfg.num_tref + cfg.num_bins, "trajectories must be [B, R+nb, n, 2]"
-        assert ev.dim() == 3 and ev.shape[0] == B and ev.shape[2] == 6, "events must be [B, M, 6]"
+        packed = seg_start is not None
+        if packed:       # io.PackedEvents: records [B, M, 4] + seg_start [B, G*NT+1]
+            assert ev.dim() == 3 and ev.shape[0] == B and ev.shape[2] == 4, "records must be [B, M, 4]"
+            seg = seg_start.detach().to(device=dev, dtype=torch.int32).contiguous()
+            _, nty, ntx, G = cabi.pack_layout(cfg)
+            assert tuple(seg.shape) == (B, G * nty * ntx + 1), "seg_start must be [B, G*NT+1]"
+        else:
+            assert ev.dim() == 3 and ev.shape[0] == B and ev.shape[2] == 6, "events must be [B, M, 6]"
+            seg = None
         assert tms.numel() == n_t
         M = ev.shape[1]
         H, W = cfg.height, cfg.width
@@ -47,13 +55,23 @@ class _CmaxLossFunction(torch.autograd.Function):
             s = cfg.lut_superpixel_size
             lut = torch.empty((B, cfg.num_bins, (H + s - 1) // s, (W + s - 1) // s, cfg.num_tref, 2),
                               dtype=torch.float32, device=dev)
-        rc = lib.cmax_forward(cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev), B, M, n,
-                              int(num_pos_events), cabi.ptr(iwes), cabi.ptr(losses), cabi.ptr(lut),
-                              cabi.ptr(ws), need, cabi.stream_ptr(dev))
-        cabi.check(rc, "cmax_forward")
+        if packed:
+            rc = lib.cmax_forward_packed(cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev), cabi.ptr(seg),
+                                         B, M, n, cabi.ptr(iwes), cabi.ptr(losses), cabi.ptr(lut),
+                                         cabi.ptr(ws), need, cabi.stream_ptr(dev))
+            cabi.check(rc, "cmax_forward_packed")
+        else:
+            rc = lib.cmax_forward(cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev), B, M, n,
+                                  int(num_pos_events), cabi.ptr(iwes), cabi.ptr(losses), cabi.ptr(lut),
+                                  cabi.ptr(ws), need, cabi.stream_ptr(dev))
+            cabi.check(rc, "cmax_forward")
         ctx.cfg = cfg
         ctx.dims = (B, M, n, int(num_pos_events), need)
-        ctx.save_for_backward(traj, tms, ev, ws)
+        ctx.packed = packed
+        if packed:
+            ctx.save_for_backward(traj, tms, ev, ws, seg)
+        else:
+            ctx.save_for_backward(traj, tms, ev, ws)
         ctx.mark_non_differentiable(iwes, losses)
         if lut is not None:
             ctx.mark_non_differentiable(lut)
@@ -63,15 +81,22 @@ class _CmaxLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, *unused):
         lib = cabi.load()
-        traj, tms, ev, ws = ctx.saved_tensors
+        traj, tms, ev, ws = ctx.saved_tensors[:4]
         B, M, n, npos, need = ctx.dims
         g = grad_loss.detach().to(device=traj.device, dtype=torch.float32).reshape(1).contiguous()
         dtraj = torch.empty_like(traj)
-        rc = lib.cmax_backward(ctx.cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev), B, M, n, npos,
-                               cabi.ptr(g), cabi.ptr(dtraj), cabi.ptr(ws), need,
-                               cabi.stream_ptr(traj.device))
-        cabi.check(rc, "cmax_backward")
-        return dtraj, None, None, None, None, None
+        if ctx.packed:
+            seg = ctx.saved_tensors[4]
+            rc = lib.cmax_backward_packed(ctx.cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev),
+                                          cabi.ptr(seg), B, M, n, cabi.ptr(g), cabi.ptr(dtraj),
+                                          cabi.ptr(ws), need, cabi.stream_ptr(traj.device))
+            cabi.check(rc, "cmax_backward_packed")
+        else:
+            rc = lib.cmax_backward(ctx.cfg, cabi.ptr(traj), cabi.ptr(tms), cabi.ptr(ev), B, M, n, npos,
+                                   cabi.ptr(g), cabi.ptr(dtraj), cabi.ptr(ws), need,
+                                   cabi.stream_ptr(traj.device))
+            cabi.check(rc, "cmax_backward")
+        return dtraj, None, None, None, None, None, None
 
 
 class FocusLoss(base.TrajectoryLossBase):
@@ -151,17 +176,22 @@ class FocusLoss(base.TrajectoryLossBase):
         """focus.py:66-113.
 
         trajectories [B, num_tref + num_bins, n, 2] (y, x), times [num_tref + num_bins],
-        batch {'events': [B, M, 6], 'num_pos_events': int}.
+        batch {'events': [B, M, 6], 'num_pos_events': int}; 'events' may also be an
+        `io.PackedEvents` (tile-binned loader-side layout) - same results, faster event stage.
         Returns (loss, {'focus_loss', 'smoothness_loss'}, {'iwes': ...}).
         """
         events = batch['events']
-        num_pos_events = batch['num_pos_events'] if 'num_pos_events' in batch else -1
-        assert not self.polarity_aware_batching or num_pos_events > -1
         if not (trajectories.is_cuda and events.is_cuda):
             raise RuntimeError("FocusLoss (B200) needs CUDA tensors; there is no CPU fallback")
-
-        out = _CmaxLossFunction.apply(trajectories, times, events, self._cfg,
-                                      int(num_pos_events), bool(return_flow_lut))
+        if hasattr(events, 'seg_start'):
+            # io.PackedEvents: the loader-side tile-binned layout; the polarity split is part of it
+            out = _CmaxLossFunction.apply(trajectories, times, events.records, self._cfg, 0,
+                                          bool(return_flow_lut), events.seg_start)
+        else:
+            num_pos_events = batch['num_pos_events'] if 'num_pos_events' in batch else -1
+            assert not self.polarity_aware_batching or num_pos_events > -1
+            out = _CmaxLossFunction.apply(trajectories, times, events, self._cfg,
+                                          int(num_pos_events), bool(return_flow_lut))
         loss, losses, iwes = out[0], out[1], out[2]
 
         h, w = self.image_shape

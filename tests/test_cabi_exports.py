@@ -68,7 +68,7 @@ def test_error_codes_without_gpu():
     big_k = cabi.make_config(**dict(synthetic.DSEC_LOSS_CONFIG, num_knn=500))
     assert lib.cmax_workspace_bytes(big_k, 1, 10, 19200) == 0
     assert lib.cmax_create_iwe(None, None, 1, 10, 1, 4, 4, 0.0, None, None, None, 0, None) == -2
-    assert lib.cmax_stage_count() == 12 and lib.cmax_stage_name(1) == b"knn_select"
+    assert lib.cmax_stage_count() == 13 and lib.cmax_stage_name(1) == b"knn_select"
     with pytest.raises(ValueError):
         cabi.make_config(**dict(synthetic.DSEC_LOSS_CONFIG, focus_loss_norm="l3"))
 

@@ -1,0 +1,243 @@
+"""Packed, tile-binned event layout (include/cmax_b200.h).
+
+CPU part: the host packer (`io.pack_events_host`) against a brute-force restatement of the
+layout contract, and its round trip.  GPU part (-m gpu, through the C ABI): the tile kernels
+(`cmax_forward_packed` / `cmax_backward_packed`) against the reference goldens, against the
+float64 oracle, and - in deterministic mode, where sums are order independent - BIT-IDENTICAL to
+the unpacked path; the device packer against the host packer.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import LOSS_CASES, load_case, rel_err
+
+TOL = 1e-5
+
+
+def _cfg(d, **kw):
+    from motionpriorcmax_b200 import cabi
+    keys = ("image_shape", "num_tref", "num_bins", "num_knn", "smooth_weight", "lut_superpixel_size",
+            "focus_loss_norm", "dist_norm", "scale_iwe_by_dt", "mask_image_border",
+            "polarity_aware_batching", "interpolation_scheme", "smooth_type")
+    return cabi.make_config(**{k: d[k] for k in keys}, **kw)
+
+
+def _segments(packed, layout):
+    """{(b, segment): sorted list of (y, x, t, meta) tuples}"""
+    ct, nty, ntx, G = layout
+    rec = packed.records.cpu().numpy()
+    seg = packed.seg_start.cpu().numpy()
+    out = {}
+    for b in range(rec.shape[0]):
+        for k in range(G * nty * ntx):
+            a, e = seg[b, k], seg[b, k + 1]
+            if e > a:
+                rows = rec[b, a:e].view(np.uint32)
+                out[(b, k)] = sorted(map(tuple, rows.tolist()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU: host packer
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s,pab", [(4, True), (3, False), (8, True), (64, False)])
+def test_host_packer_layout_contract(s, pab):
+    from motionpriorcmax_b200 import io, synthetic
+    H, W, nb = 50, 70, 5
+    d = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(H, W), num_bins=nb, lut_superpixel_size=s,
+             num_knn=2, polarity_aware_batching=pab)
+    cfg = _cfg(d)
+    ct = max(32 // s, 1)
+    Hq, Wq = -(-H // s), -(-W // s)
+    layout = (ct, -(-Hq // ct), -(-Wq // ct), 2 if pab else 1)
+    ev, npos = synthetic.make_event_batch(3, [700, 300, 0], H, W, nb, pab, seed=3)
+    ev = ev.clone()
+    # adversarial rows: coordinates a few ulp around cell edges, outside the table, NaN, padding
+    ev[0, 0, :2] = torch.tensor([np.float32(s) - np.float32(1e-6), 2.0 * s])
+    ev[0, 1, :2] = torch.tensor([-0.5, 3.0])              # iy = -1 -> dropped
+    ev[0, 2, :2] = torch.tensor([float(H + 3 * s), 1.0])  # iy >= Hq -> dropped
+    ev[0, 3, 0] = float("nan")                            # dropped
+    ev[0, 4, 4] = float(nb)                               # bin out of range -> dropped
+    ev[0, 5, 5] = 0.0                                     # padding row
+    pk = io.pack_events_host(ev, npos, cfg, layout=layout)
+    G, nt = layout[3], layout[1] * layout[2]
+    assert pk.seg_start.shape == (3, G * nt + 1) and pk.seg_start.dtype == torch.int32
+    assert pk.records.dtype == torch.float32 and pk.records.shape[2] == 4
+    # brute force, with the reference's own index arithmetic (focus.py:185-187)
+    want = {}
+    dropped = 0
+    for b in range(3):
+        for m in range(ev.shape[1]):
+            y, x, t, _, bn, v = (ev[b, m, k] for k in range(6))
+            if v == 0:
+                continue
+            it, iy, ix = bn.to(torch.int64) if bn == bn else torch.tensor(-1), y // s, x // s
+            if not (bn == bn and 0 <= it < nb and 0 <= iy < Hq and 0 <= ix < Wq):
+                dropped += 1
+                continue
+            it, iy, ix = int(it), int(iy), int(ix)
+            g = 1 if (pab and m >= npos) else 0
+            k = g * nt + (iy // ct) * layout[2] + ix // ct
+            meta = (it << 24) | (iy << 12) | ix
+            row = tuple(np.array([y, x, t], np.float32).view(np.uint32).tolist()) + (meta,)
+            want.setdefault((b, k), []).append(row)
+    want = {k: sorted(v) for k, v in want.items()}
+    assert dropped >= 4 and int(pk.skipped[0]) == dropped
+    assert _segments(pk, layout) == want
+    assert pk.seg_start[:, -1].tolist() == [sum(len(v) for (b, _), v in want.items() if b == i) for i in range(3)]
+    # round trip: unpack -> pack gives the same segments
+    ev2, npos2 = io.unpack_events(pk, cfg, layout=layout)
+    pk2 = io.pack_events_host(ev2, npos2, cfg, layout=layout)
+    assert _segments(pk2, layout) == want
+
+
+def test_pack_layout_query_and_limits():
+    from motionpriorcmax_b200 import cabi, synthetic
+    lib = cabi.load()
+    cfg = _cfg(synthetic.DSEC_LOSS_CONFIG)
+    assert cabi.pack_layout(cfg) == (8, 15, 20, 2)
+    ev = _cfg(synthetic.EVIMO2_LOSS_CONFIG)
+    assert cabi.pack_layout(ev) == (8, 12, 16, 2)
+    big = _cfg(dict(synthetic.DSEC_LOSS_CONFIG, num_bins=300))
+    out = (cabi.c_int32 * 4)()
+    assert lib.cmax_pack_layout(big, out) == -5        # CMAX_ERR_UNSUPPORTED: bin does not fit the meta word
+    assert lib.cmax_pack_layout(None, out) == -1
+    # argument validation of the packed entry points without a GPU
+    assert lib.cmax_forward_packed(cfg, None, None, None, None, 1, 10, 19200, None, None, None, None, 0, None) == -2
+    assert lib.cmax_backward_packed(cfg, None, None, None, None, 1, 10, 19200, None, None, None, 0, None) == -2
+    assert lib.cmax_pack_events(cfg, None, 1, 10, 5, None, None, None, None, None) == -2
+
+
+# ------------------------------------------------------------------------------------------
+# GPU
+# ------------------------------------------------------------------------------------------
+def _cuda():
+    assert torch.cuda.is_available(), "these tests need a GPU (run with -m gpu on a B200)"
+    return torch.device("cuda:0")
+
+
+def _run(cfg, traj, times, events, npos, mode, deterministic=False):
+    """mode: 'plain' (upstream layout), 'packed_dev' (cmax_pack_events), 'packed_host'."""
+    from motionpriorcmax_b200 import io
+    from motionpriorcmax_b200.losses import LossFactory
+    dev = _cuda()
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=deterministic))
+    t = torch.as_tensor(traj, device=dev).clone().requires_grad_()
+    ev = torch.as_tensor(events)
+    if mode == "plain":
+        batch = {"events": ev.to(dev)}
+        if npos >= 0:
+            batch["num_pos_events"] = npos
+    elif mode == "packed_dev":
+        batch = {"events": io.pack_events(ev.to(dev), npos if npos >= 0 else None, L)}
+    else:
+        batch = {"events": io.pack_events_host(ev, npos if npos >= 0 else None, L).to(dev)}
+    loss, log, misc = L.calc(t, torch.as_tensor(times, device=dev), batch, return_flow_lut=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(loss=loss.item(), focus=log["focus_loss"].item(), smooth=log["smoothness_loss"].item(),
+                iwes=misc["iwes"].cpu().numpy(), lut=misc["flow_lut"].cpu().numpy(),
+                dtraj=t.grad.cpu().numpy(), packed=batch["events"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LOSS_CASES)
+@pytest.mark.parametrize("mode", ["packed_dev", "packed_host"])
+def test_packed_matches_reference_golden(name, mode):
+    from test_gpu_parity import _assert_grad_close
+    c = load_case(name)
+    r = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], mode)
+    assert abs(r["loss"] - float(c["loss"])) <= TOL * abs(float(c["loss"]))
+    assert abs(r["focus"] - float(c["focus_loss"])) <= TOL * abs(float(c["focus_loss"]))
+    assert rel_err(r["iwes"], c["iwes"]) < TOL
+    _assert_grad_close(r["dtraj"], c["dtraj"], c["cfg"], c["trajectories"], c["times"], c["events"],
+                       c["num_pos_events"], tol=TOL, gpu_iwes=r["iwes"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_packed_deterministic_is_bit_identical_to_unpacked(name):
+    """int64 fixed-point sums do not depend on the order or the grouping of the events: the tile
+    kernels must reproduce the unpacked kernels bit for bit (IWE, loss, gradients)."""
+    c = load_case(name)
+    a = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], "plain", True)
+    for mode in ("packed_dev", "packed_host"):
+        b = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], mode, True)
+        assert a["loss"] == b["loss"] and a["focus"] == b["focus"]
+        assert np.array_equal(a["iwes"], b["iwes"])
+        assert np.array_equal(a["dtraj"], b["dtraj"])
+
+
+@pytest.mark.gpu
+def test_device_packer_equals_host_packer():
+    from motionpriorcmax_b200 import cabi, io, synthetic
+    dev = _cuda()
+    for d, B, M in ((dict(synthetic.DSEC_LOSS_CONFIG), 3, [150_000, 40_000, 0]),
+                    (dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(50, 70), lut_superpixel_size=3,
+                          polarity_aware_batching=False, num_bins=5, num_knn=2), 2, [5000, 7000])):
+        cfg = _cfg(d)
+        H, W = d["image_shape"]
+        ev, npos = synthetic.make_event_batch(B, M, H, W, d["num_bins"], d["polarity_aware_batching"], seed=8)
+        ev = ev.clone()
+        ev[0, :50, 0] = -1.0                  # outside the table
+        ev[1, 10:20, 4] = 99.0                # bin out of range
+        ev[0, 100, 1] = float("inf")
+        layout = cabi.pack_layout(cfg)
+        host = io.pack_events_host(ev, npos, cfg)
+        devp = io.pack_events(ev.to(dev), npos, cfg)
+        torch.cuda.synchronize()
+        assert torch.equal(host.seg_start, devp.seg_start.cpu())
+        assert _segments(host, layout) == _segments(
+            io.PackedEvents(devp.records[:, :host.records.shape[1]], devp.seg_start), layout)
+        assert devp.skipped.cpu().tolist() == host.skipped.tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["dsec_edges", "big_flow", "multi_tref3", "s2_det", "evimo_next"])
+def test_packed_matches_oracle_midsize(variant):
+    """Mid-size windows against the float64 oracle; `big_flow` pushes most votes out of the
+    shared-memory window (global fallback), `s2_det` uses 16x16-cell tiles in fixed point."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    from test_gpu_parity import _assert_grad_close, _synthetic_case
+    base = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(96, 128), num_knn=16)
+    det, dist = False, "uniform"
+    if variant == "dsec_edges":
+        dist = "edges"
+    elif variant == "multi_tref3":
+        base = synthetic.multi_tref_variant(base, 3)
+    elif variant == "s2_det":
+        base.update(lut_superpixel_size=2)
+        det = True
+    elif variant == "evimo_next":
+        base.update(smooth_type="on_flow_to_next", smooth_weight=0.06, num_bins=9)
+    traj, times, ev, npos, _ = _synthetic_case(base, 3, [20000, 35000, 9000], 2, seed=21, dist=dist)
+    if variant == "big_flow":
+        pos = traj[:, -1:, :, :] * 0 + fo.tile_positions((96, 128), 4).astype(np.float32)[None, None]
+        traj = (pos + (traj - pos) * 6.0).astype(np.float32)        # flows of several tens of pixels
+    r = _run(base, traj, times, ev, npos, "packed_dev", det)
+    o = fo.FocusOracle(**base, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert abs(r["smooth"] - f["smoothness_loss"]) <= TOL * max(abs(f["smoothness_loss"]), 1e-3)
+    assert rel_err(r["iwes"], f["iwes"]) < TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], base, traj, times, ev, npos, gpu_iwes=r["iwes"])
+
+
+@pytest.mark.gpu
+def test_packed_full_size_properties():
+    """DSEC-size batch: deterministic packed == deterministic unpacked bit for bit, with large
+    segments (slices per tile) and one empty window; float mode within tolerance."""
+    from motionpriorcmax_b200 import synthetic
+    from test_gpu_parity import _synthetic_case
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 3, [1_500_000, 300_000, 0], 1, seed=31)
+    a = _run(cfg, traj, times, ev, npos, "plain", True)
+    b = _run(cfg, traj, times, ev, npos, "packed_dev", True)
+    assert a["loss"] == b["loss"]
+    assert np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
+    c = _run(cfg, traj, times, ev, npos, "packed_dev", False)
+    assert abs(a["loss"] - c["loss"]) <= TOL * abs(a["loss"])
+    assert rel_err(c["iwes"], a["iwes"]) < TOL and rel_err(c["dtraj"], a["dtraj"]) < TOL
