@@ -406,6 +406,8 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
 static int pack_supported(const Geom &g)
 {
     if (g.nb > 256 || g.Hq > 4096 || g.Wq > 4096 || g.M > (int64_t)INT32_MAX) return CMAX_ERR_UNSUPPORTED;
+    if ((int64_t)g.P * g.nt > 12288) return CMAX_ERR_UNSUPPORTED;     // segment counters live in 48 KB of smem
+    if (g.S * (int64_t)g.q * g.R >= (int64_t)INT32_MAX / 2) return CMAX_ERR_UNSUPPORTED;   // 32-bit LUT indices
     return CMAX_OK;
 }
 

@@ -381,6 +381,25 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
             const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
             return L1D ? __fadd_rn(fabsf(dy), fabsf(dx)) : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
         };
+        // Columns of window row `lr` that can hold a point with d < hi: the row's cells are clipped
+        // to the disc (l1: diamond) of that radius around the query - about half of the square
+        // window.  Conservative by 1e-5 relative, like window_bound: cells are assigned with a
+        // rounded product, boundary cells also hold everything beyond the grid (cell_of clamps).
+        auto row_span = [&](int lr, float hi, int c0w, int c1w, int &a, int &e) -> bool {
+            const int row = wy0 + lr;
+            float dym = row < cqy ? qy - (float)(row + 1) * g.cs : (row > cqy ? (float)row * g.cs - qy : 0.0f);
+            dym = fmaxf(dym, 0.0f) * (1.0f - 1e-5f);
+            const float rem = L1D ? hi - dym : hi - dym * dym;
+            if (!(rem > 0.0f)) return false;
+            const float hw = (L1D ? rem : sqrtf(rem)) * (1.0f + 1e-5f) + 1e-6f;
+            const float cl = fminf(fmaxf(floorf((qx - hw) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
+            const float ch = fminf(fmaxf(floorf((qx + hw) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
+            const int c0 = max((int)cl - wx0, c0w), c1 = min((int)ch - wx0 + 1, c1w);
+            if (c0 >= c1) return false;
+            a = s_cell[lr][c0];
+            e = s_cell[lr][c1];
+            return true;
+        };
         if (GUESS) {
             // K-th key of the same cell in the previous bin as left by the *fast* kernel (NaN where
             // it was not settled there - then a direct neighbour's value serves as the guess)
@@ -420,7 +439,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                                : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
                 };
                 for (int lr = r0w; lr <= r1w; ++lr) {
-                    const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                    int a, e;
+                    if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
                     int i = a;
                     for (; i + 4 <= e; i += 4) {          // distances first (4 loads in flight)
                         const float d0 = dist_at(i), d1 = dist_at(i + 1), d2 = dist_at(i + 2),
@@ -487,7 +507,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 // ---- pass 1: histogram ---------------------------------------------------------
                 unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit
                 for (int lr = r0w; lr <= r1w; ++lr) {
-                    const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                    int a, e;
+                    if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
                     for (int i = a; i < e; ++i) {
                         const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
                         const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
@@ -508,7 +529,8 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
                 if (bstar >= 0 && in_b <= kListCap) {
                     // ---- pass 2: accumulate sure members, collect the boundary bucket ------------
                     for (int lr = r0w; lr <= r1w; ++lr) {
-                        const int a = s_cell[lr][c0w], e = s_cell[lr][c1w];
+                        int a, e;
+                        if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
                         for (int i = a; i < e; ++i) {
                             const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
                             const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))

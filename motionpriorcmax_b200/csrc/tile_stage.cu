@@ -59,23 +59,43 @@ __device__ __forceinline__ bool pack_key(const EventRow &e, const Geom &g, int64
     return true;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kPackThreads = 512;
+constexpr int kPackRows = 8;                            // rows per thread: a CTA bins 4096 rows
+
+// Histogram of one 4096-row chunk in shared memory, then one global add per non-empty segment
+// (a global atomic per event serialises on the few hundred counters of a sample).
+__global__ void __launch_bounds__(kPackThreads)
 pack_count_kernel(const float *__restrict__ events, Geom g, int *__restrict__ counts,
                   long long *__restrict__ skipped)
 {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int s_hist[];
+    const int nkeys = g.P * g.nt;
     const int64_t b = blockIdx.y;
-    if (m >= g.M) return;
-    const EventRow e = load_event(events + (b * g.M + m) * 6);
-    if (e.valid == 0.0f) return;
-    int key;
-    unsigned meta;
-    if (!pack_key(e, g, m, &key, &meta)) {
-        if (skipped) atomicAdd(reinterpret_cast<unsigned long long *>(skipped), 1ull);
-        return;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nkeys; k += kPackThreads) s_hist[k] = 0;
+    __syncthreads();
+    int n_out = 0, n_odd = 0;
+#pragma unroll
+    for (int u = 0; u < kPackRows; ++u) {
+        const int64_t m = ((int64_t)blockIdx.x * kPackRows + u) * kPackThreads + tid;
+        if (m >= g.M) continue;
+        const EventRow e = load_event(events + (b * g.M + m) * 6);
+        if (e.valid == 0.0f) continue;
+        int key;
+        unsigned meta;
+        if (!pack_key(e, g, m, &key, &meta)) { ++n_out; continue; }
+        if (e.valid != 1.0f) ++n_odd;
+        atomicAdd(&s_hist[key], 1);
     }
-    if (e.valid != 1.0f && skipped) atomicAdd(reinterpret_cast<unsigned long long *>(skipped + 1), 1ull);
-    atomicAdd(counts + b * (int64_t)(g.P * g.nt) + key, 1);
+    __syncthreads();
+    for (int k = tid; k < nkeys; k += kPackThreads) {
+        const int c = s_hist[k];
+        if (c) atomicAdd(counts + b * (int64_t)nkeys + k, c);
+    }
+    if (skipped) {
+        if (n_out) atomicAdd(reinterpret_cast<unsigned long long *>(skipped), (unsigned long long)n_out);
+        if (n_odd) atomicAdd(reinterpret_cast<unsigned long long *>(skipped + 1), (unsigned long long)n_odd);
+    }
 }
 
 // one CTA per sample: exclusive scan of the G*NT counters -> seg_start, cursors
@@ -124,20 +144,45 @@ pack_scan_kernel(Geom g, int *__restrict__ counts, int *__restrict__ seg_start)
     if (tid == 0) out[n] = carry;
 }
 
-__global__ void __launch_bounds__(256)
+// Same chunking: local ranks from the shared-memory histogram, one global cursor reservation per
+// non-empty segment of the chunk, then the records are written to their final slots.
+__global__ void __launch_bounds__(kPackThreads)
 pack_scatter_kernel(const float *__restrict__ events, Geom g, int *__restrict__ cursor,
                     float4 *__restrict__ records)
 {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int s_hist[];
+    const int nkeys = g.P * g.nt;
     const int64_t b = blockIdx.y;
-    if (m >= g.M) return;
-    const EventRow e = load_event(events + (b * g.M + m) * 6);
-    if (e.valid == 0.0f) return;
-    int key;
-    unsigned meta;
-    if (!pack_key(e, g, m, &key, &meta)) return;
-    const int pos = atomicAdd(cursor + b * (int64_t)(g.P * g.nt) + key, 1);
-    records[b * g.M + pos] = make_float4(e.y, e.x, e.t, __uint_as_float(meta));
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nkeys; k += kPackThreads) s_hist[k] = 0;
+    __syncthreads();
+    float ry[kPackRows], rx[kPackRows], rt[kPackRows];
+    int key[kPackRows], rank[kPackRows];
+    unsigned meta[kPackRows];
+#pragma unroll
+    for (int u = 0; u < kPackRows; ++u) {
+        key[u] = -1;
+        const int64_t m = ((int64_t)blockIdx.x * kPackRows + u) * kPackThreads + tid;
+        if (m >= g.M) continue;
+        const EventRow e = load_event(events + (b * g.M + m) * 6);
+        if (e.valid == 0.0f) continue;
+        int k;
+        if (!pack_key(e, g, m, &k, &meta[u])) continue;
+        key[u] = k;
+        ry[u] = e.y; rx[u] = e.x; rt[u] = e.t;
+        rank[u] = atomicAdd(&s_hist[k], 1);
+    }
+    __syncthreads();
+    for (int k = tid; k < nkeys; k += kPackThreads) {
+        const int c = s_hist[k];
+        if (c) s_hist[k] = atomicAdd(cursor + b * (int64_t)nkeys + k, c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPackRows; ++u)
+        if (key[u] >= 0)
+            records[b * g.M + s_hist[key[u]] + rank[u]] =
+                make_float4(ry[u], rx[u], rt[u], __uint_as_float(meta[u]));
 }
 
 int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
@@ -145,13 +190,15 @@ int launch_pack_events(const Geom &g, const float *events, float4 *records, int 
 {
     StageScope sc(ST_PACK, st);
     const int n = g.P * g.nt;
+    const size_t sm = sizeof(int) * n;
     cudaMemsetAsync(scratch, 0, sizeof(int) * g.B * n, st);
     if (skipped) cudaMemsetAsync(skipped, 0, sizeof(long long) * 2, st);
-    dim3 grid((unsigned)((g.M + 255) / 256), (unsigned)g.B);
+    const int64_t chunk = (int64_t)kPackThreads * kPackRows;
+    dim3 grid((unsigned)((g.M + chunk - 1) / chunk), (unsigned)g.B);
     count_launch(g.M > 0 ? 3 : 1);
-    if (g.M > 0) pack_count_kernel<<<grid, 256, 0, st>>>(events, g, scratch, skipped);
+    if (g.M > 0) pack_count_kernel<<<grid, kPackThreads, sm, st>>>(events, g, scratch, skipped);
     pack_scan_kernel<<<(unsigned)g.B, 1024, 0, st>>>(g, scratch, seg_start);
-    if (g.M > 0) pack_scatter_kernel<<<grid, 256, 0, st>>>(events, g, scratch, records);
+    if (g.M > 0) pack_scatter_kernel<<<grid, kPackThreads, sm, st>>>(events, g, scratch, records);
     return check_launch();
 }
 
@@ -179,49 +226,49 @@ __device__ __forceinline__ Seg cta_segment(const Geom &g, const int *__restrict_
 }
 
 // Window origin for reference time r: the tile's pixel box grown by the range of the flows stored
-// in the tile's LUT block (all bins).  Only a placement heuristic - votes outside the window take
-// the global path - so forward and backward need not agree and NaN / huge flows are harmless.
+// in the tile's LUT block, sampled on a 3 x 3 lattice of its cells in every bin (the LUT is a
+// K-neighbour mean, i.e. smooth inside a 32-pixel tile).  Only a placement heuristic - votes
+// outside the window take the global path - so forward and backward need not agree and NaN /
+// huge flows are harmless.  Computed by warp 0, broadcast through shared memory.
 __device__ __forceinline__ void window_origin(const Geom &g, const float *__restrict__ lut, int64_t b,
-                                              const Seg &s, int r, float *s_red, int *oy, int *ox)
+                                              const Seg &s, int r, int *s_org, int *oy, int *ox)
 {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    float mny = INFINITY, mxy = -INFINITY, mnx = INFINITY, mxx = -INFINITY;
-    const int cc = g.ct * g.ct, tot = cc * g.nb;
-    for (int i = tid; i < tot; i += kTileThreads) {
-        const int bin = i / cc, c = i - bin * cc;
-        const int iy = s.ty * g.ct + c / g.ct, ix = s.tx * g.ct + c % g.ct;
-        if (iy < g.Hq && ix < g.Wq) {
-            const int64_t cell = ((b * g.nb + bin) * g.Hq + iy) * g.Wq + ix;
-            const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
-            mny = fminf(mny, f.x); mxy = fmaxf(mxy, f.x);
-            mnx = fminf(mnx, f.y); mxx = fmaxf(mxx, f.y);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float mny = INFINITY, mxy = -INFINITY, mnx = INFINITY, mxx = -INFINITY;
+        const int y0 = s.ty * g.ct, x0 = s.tx * g.ct;
+        const int y2 = min(y0 + g.ct, g.Hq) - 1, x2 = min(x0 + g.ct, g.Wq) - 1;
+        const int ys[3] = {y0, (y0 + y2) >> 1, y2}, xs[3] = {x0, (x0 + x2) >> 1, x2};
+        for (int bin = lane; bin < g.nb; bin += 32) {
+            const float2 *base = reinterpret_cast<const float2 *>(lut) + ((b * g.nb + bin) * (int64_t)g.q) * g.R + r;
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const float2 f = __ldg(base + (int64_t)(ys[u / 3] * g.Wq + xs[u % 3]) * g.R);
+                mny = fminf(mny, f.x); mxy = fmaxf(mxy, f.x);
+                mnx = fminf(mnx, f.y); mxx = fmaxf(mxx, f.y);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        }
+        if (lane == 0) {
+            const int tp = g.ct * g.s;
+            auto place = [&](int t0, float mn, float mx) {
+                if (!(mn > -1e6f && mx < 1e6f)) return t0 - (kWin - tp) / 2;
+                const int lo = t0 + (int)floorf(mn) - 2, hi = t0 + tp + (int)ceilf(mx) + 3;
+                return hi - lo <= kWin ? lo : (lo + hi) / 2 - kWin / 2;
+            };
+            s_org[0] = place(s.ty * tp, mny, mxy);
+            s_org[1] = place(s.tx * tp, mnx, mxx) & ~3;     // quads of the flush stay 16-byte aligned
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-    }
-    if (lane == 0) {
-        s_red[wid * 4 + 0] = mny; s_red[wid * 4 + 1] = mxy;
-        s_red[wid * 4 + 2] = mnx; s_red[wid * 4 + 3] = mxx;
-    }
     __syncthreads();
-    for (int w = 0; w < kTileThreads / 32; ++w) {
-        mny = fminf(mny, s_red[w * 4 + 0]); mxy = fmaxf(mxy, s_red[w * 4 + 1]);
-        mnx = fminf(mnx, s_red[w * 4 + 2]); mxx = fmaxf(mxx, s_red[w * 4 + 3]);
-    }
-    __syncthreads();
-    const int tp = g.ct * g.s;
-    auto place = [&](int t0, float mn, float mx) {
-        if (!(mn > -1e6f && mx < 1e6f)) return t0 - (kWin - tp) / 2;
-        const int lo = t0 + (int)floorf(mn) - 1, hi = t0 + tp + (int)ceilf(mx) + 2;
-        return hi - lo <= kWin ? lo : (lo + hi) / 2 - kWin / 2;
-    };
-    *oy = place(s.ty * tp, mny, mxy);
-    *ox = place(s.tx * tp, mnx, mxx) & ~3;          // quads of the flush stay 16-byte aligned
+    *oy = s_org[0];
+    *ox = s_org[1];
 }
 
 struct PackedEvent {
@@ -271,7 +318,7 @@ __device__ __forceinline__ Corners2 vote_corners2(float wy, float wx, int H, int
 // forward
 // ---------------------------------------------------------------------------------------------
 template <bool DET>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 6)
 event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restrict__ seg_start,
                           const float *__restrict__ times, Geom g, int split,
                           const float *__restrict__ lut, float *__restrict__ raw,
@@ -280,7 +327,7 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
     using Acc = typename std::conditional<DET, unsigned long long, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Acc *s_win = reinterpret_cast<Acc *>(smem_raw);
-    __shared__ float s_red[4 * kTileThreads / 32];
+    __shared__ int s_org[2];
 
     const Seg sg = cta_segment(g, seg_start, split);
     if (sg.a >= sg.e) return;
@@ -290,35 +337,54 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
     const float4 *recs = records + b * g.M;
     const bool use_win = sg.e - sg.a >= 64;              // tiny slices: global reds are cheaper
 
+    const int lut_base = (int)b * g.nb;
     for (int r = 0; r < g.R; ++r) {
         int oy = 0, ox = 0;
         if (use_win) {
-            window_origin(g, lut, b, sg, r, s_red, &oy, &ox);
             for (int i = tid; i < kWin * kWin; i += kTileThreads) s_win[i] = (Acc)0;
-            __syncthreads();
+            window_origin(g, lut, b, sg, r, s_org, &oy, &ox);       // ends with a barrier
         }
+        // window entirely inside the image: every corner that is in the window is in bounds
+        const bool interior = use_win && oy >= 0 && oy + kWin <= g.H && ox >= 0 && ox + kWin <= g.W;
+        const float wy0 = use_win ? (float)oy : 1e30f, wy1 = (float)(oy + kWin - 1);
+        const float wx0 = (float)ox, wx1 = (float)(ox + kWin - 1);
         const float tref = __ldg(times + r);
         const int64_t base = ((b * g.R + r) * g.P + sg.grp) * HW;
         for (int i = sg.a + tid; i < sg.e; i += kTileThreads) {
             const PackedEvent pe = unpack(ld_stream_f4(recs + i));
             if (pe.bin >= g.nb || pe.iy >= g.Hq || pe.ix >= g.Wq) continue;      // corrupt record
-            const int64_t cell = ((b * g.nb + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
+            const int cell = ((lut_base + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
             const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
             const float wy = __fadd_rn(f.x, pe.e.y), wx = __fadd_rn(f.y, pe.e.x);     // focus.py:191
             const float w = event_weight(pe.e, wy, wx, tref, g);
             if (w == 0.0f) continue;
-            const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
-            if (!c.finite) continue;
-            const float oyw = __fsub_rn(1.0f, c.fy), oxw = __fsub_rn(1.0f, c.fx);
+            const float y1 = floorf(__fadd_rn(wy, kVoteEps)), x1 = floorf(__fadd_rn(wx, kVoteEps));
+            const float fy = __fsub_rn(wy, y1), fx = __fsub_rn(wx, x1);
+            const float oyw = __fsub_rn(1.0f, fy), oxw = __fsub_rn(1.0f, fx);
             float v[4];
             v[0] = __fmul_rn(__fmul_rn(oyw, oxw), w);        // event_image_converter.py:382-385
-            v[1] = __fmul_rn(__fmul_rn(c.fy, oxw), w);
-            v[2] = __fmul_rn(__fmul_rn(oyw, c.fx), w);
-            v[3] = __fmul_rn(__fmul_rn(c.fy, c.fx), w);
+            v[1] = __fmul_rn(__fmul_rn(fy, oxw), w);
+            v[2] = __fmul_rn(__fmul_rn(oyw, fx), w);
+            v[3] = __fmul_rn(__fmul_rn(fy, fx), w);
+            const bool in_win = y1 >= wy0 && y1 < wy1 && x1 >= wx0 && x1 < wx1;
+            if (in_win && interior) {
+                Acc *p = s_win + ((int)y1 - oy) * kWin + ((int)x1 - ox);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    Acc *q = p + (k & 1) * kWin + (k >> 1);
+                    if (DET)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(q),
+                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                    else
+                        atomicAdd(reinterpret_cast<float *>(q), v[k]);
+                }
+                continue;
+            }
+            const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
+            if (!c.finite) continue;
             const bool ok[4] = {c.y0ok && c.x0ok, c.y1ok && c.x0ok, c.y0ok && c.x1ok, c.y1ok && c.x1ok};
-            const int ly = c.y - oy, lx = c.x - ox;
-            if (use_win && ly >= 0 && ly < kWin - 1 && lx >= 0 && lx < kWin - 1) {
-                Acc *p = s_win + ly * kWin + lx;
+            if (in_win) {
+                Acc *p = s_win + (c.y - oy) * kWin + (c.x - ox);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (!ok[k]) continue;
@@ -378,7 +444,7 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
 // backward
 // ---------------------------------------------------------------------------------------------
 template <bool DET>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 6)
 event_backward_tile_kernel(const float4 *__restrict__ records, const int *__restrict__ seg_start,
                            const float *__restrict__ times, Geom g, int split, int smem_acc,
                            const float *__restrict__ lut, const float *__restrict__ dimg,
@@ -389,7 +455,7 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_D = reinterpret_cast<float *>(smem_raw);                       // [kWin * kWin]
     Acc *s_acc = reinterpret_cast<Acc *>(smem_raw + sizeof(float) * kWin * kWin);   // [nb, ct, ct, 2]
-    __shared__ float s_red[4 * kTileThreads / 32];
+    __shared__ int s_org[2];
 
     const Seg sg = cta_segment(g, seg_start, split);
     if (sg.a >= sg.e) return;
@@ -407,48 +473,70 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
         coef = __ldg(grad_loss) * (-(1.0f / (val * val))) / N;
     }
 
+    const int lut_base = (int)b * g.nb;
     for (int r = 0; r < g.R; ++r) {
         const float *D = dimg + ((b * g.R + r) * g.P + sg.grp) * HW;
         int oy = 0, ox = 0;
         if (use_win) {
-            window_origin(g, lut, b, sg, r, s_red, &oy, &ox);
-            for (int i = tid; i < kWin * kWin; i += kTileThreads) {
-                const int gy = oy + i / kWin, gx = ox + i % kWin;
-                s_D[i] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? __ldg(D + (int64_t)gy * g.W + gx) : 0.0f;
-            }
             if (use_acc)
                 for (int i = tid; i < nacc * 2; i += kTileThreads) s_acc[i] = (Acc)0;
+            window_origin(g, lut, b, sg, r, s_org, &oy, &ox);
+            // stage dL/dIWE of the window (zero outside the image)
+            if ((g.W & 3) == 0 && ((((b * g.R + r) * g.P + sg.grp) * HW) & 3) == 0) {
+                for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
+                    const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));   // ox % 4 == 0
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+                        v = __ldg(reinterpret_cast<const float4 *>(D + (int64_t)gy * g.W + gx));
+                    reinterpret_cast<float4 *>(s_D)[i] = v;
+                }
+            } else {
+                for (int i = tid; i < kWin * kWin; i += kTileThreads) {
+                    const int gy = oy + i / kWin, gx = ox + i % kWin;
+                    s_D[i] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? __ldg(D + (int64_t)gy * g.W + gx) : 0.0f;
+                }
+            }
             __syncthreads();
         }
+        const bool interior = use_win && oy >= 0 && oy + kWin <= g.H && ox >= 0 && ox + kWin <= g.W;
+        const float wy0 = use_win ? (float)oy : 1e30f, wy1 = (float)(oy + kWin - 1);
+        const float wx0 = (float)ox, wx1 = (float)(ox + kWin - 1);
         const float tref = __ldg(times + r);
         for (int i = sg.a + tid; i < sg.e; i += kTileThreads) {
             const PackedEvent pe = unpack(ld_stream_f4(recs + i));
             if (pe.bin >= g.nb || pe.iy >= g.Hq || pe.ix >= g.Wq) continue;      // corrupt record
-            const int64_t cell = ((b * g.nb + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
+            const int cell = ((lut_base + pe.bin) * g.Hq + pe.iy) * g.Wq + pe.ix;
             const float2 f = __ldg(reinterpret_cast<const float2 *>(lut) + cell * g.R + r);
             const float wy = __fadd_rn(f.x, pe.e.y), wx = __fadd_rn(f.y, pe.e.x);
             const float w = event_weight(pe.e, wy, wx, tref, g);
             if (w == 0.0f) continue;
-            const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
-            if (!c.finite) continue;
+            const float y1 = floorf(__fadd_rn(wy, kVoteEps)), x1 = floorf(__fadd_rn(wx, kVoteEps));
+            const float fy = __fsub_rn(wy, y1), fx = __fsub_rn(wx, x1);
+            const bool in_win = y1 >= wy0 && y1 < wy1 && x1 >= wx0 && x1 < wx1;
             float d00, d10, d01, d11;
-            const int ly = c.y - oy, lx = c.x - ox;
-            if (use_win && ly >= 0 && ly < kWin - 1 && lx >= 0 && lx < kWin - 1) {
-                const float *p = s_D + ly * kWin + lx;      // zero outside the image
-                d00 = (c.y0ok && c.x0ok) ? p[0] : 0.0f;
-                d10 = (c.y1ok && c.x0ok) ? p[kWin] : 0.0f;
-                d01 = (c.y0ok && c.x1ok) ? p[1] : 0.0f;
-                d11 = (c.y1ok && c.x1ok) ? p[kWin + 1] : 0.0f;
+            if (in_win && interior) {
+                const float *p = s_D + ((int)y1 - oy) * kWin + ((int)x1 - ox);
+                d00 = p[0]; d10 = p[kWin]; d01 = p[1]; d11 = p[kWin + 1];
             } else {
-                const float *p = D + (int64_t)c.y * g.W + c.x;
-                d00 = (c.y0ok && c.x0ok) ? __ldg(p) : 0.0f;
-                d10 = (c.y1ok && c.x0ok) ? __ldg(p + g.W) : 0.0f;
-                d01 = (c.y0ok && c.x1ok) ? __ldg(p + 1) : 0.0f;
-                d11 = (c.y1ok && c.x1ok) ? __ldg(p + g.W + 1) : 0.0f;
+                const Corners2 c = vote_corners2(wy, wx, g.H, g.W);
+                if (!c.finite) continue;
+                if (in_win) {
+                    const float *p = s_D + (c.y - oy) * kWin + (c.x - ox);      // zero outside the image
+                    d00 = (c.y0ok && c.x0ok) ? p[0] : 0.0f;
+                    d10 = (c.y1ok && c.x0ok) ? p[kWin] : 0.0f;
+                    d01 = (c.y0ok && c.x1ok) ? p[1] : 0.0f;
+                    d11 = (c.y1ok && c.x1ok) ? p[kWin + 1] : 0.0f;
+                } else {
+                    const float *p = D + (int64_t)c.y * g.W + c.x;
+                    d00 = (c.y0ok && c.x0ok) ? __ldg(p) : 0.0f;
+                    d10 = (c.y1ok && c.x0ok) ? __ldg(p + g.W) : 0.0f;
+                    d01 = (c.y0ok && c.x1ok) ? __ldg(p + 1) : 0.0f;
+                    d11 = (c.y1ok && c.x1ok) ? __ldg(p + g.W + 1) : 0.0f;
+                }
             }
-            const float oyw = 1.0f - c.fy, oxw = 1.0f - c.fx;
-            const float gy = w * (oxw * (d10 - d00) + c.fx * (d11 - d01));
-            const float gx = w * (oyw * (d01 - d00) + c.fy * (d11 - d10));
+            const float oyw = 1.0f - fy, oxw = 1.0f - fx;
+            const float gy = w * (oxw * (d10 - d00) + fx * (d11 - d01));
+            const float gx = w * (oyw * (d01 - d00) + fy * (d11 - d10));
             const int cy = pe.iy - sg.ty * g.ct, cx = pe.ix - sg.tx * g.ct;
             if (use_acc && (unsigned)cy < (unsigned)g.ct && (unsigned)cx < (unsigned)g.ct) {
                 Acc *q = s_acc + 2 * ((pe.bin * g.ct + cy) * g.ct + cx);
@@ -462,11 +550,11 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
                     atomicAdd(reinterpret_cast<float *>(q) + 1, coef * gx);
                 }
             } else if (DET) {
-                unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + ((int64_t)cell * g.R + r) * 2;
                 atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
                 atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
             } else {
-                red_add_f32x2(dlut + (cell * g.R + r) * 2, coef * gy, coef * gx);
+                red_add_f32x2(dlut + ((int64_t)cell * g.R + r) * 2, coef * gy, coef * gx);
             }
         }
         if (!use_win) continue;

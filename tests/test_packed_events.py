@@ -238,6 +238,10 @@ def test_packed_full_size_properties():
     b = _run(cfg, traj, times, ev, npos, "packed_dev", True)
     assert a["loss"] == b["loss"]
     assert np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
-    c = _run(cfg, traj, times, ev, npos, "packed_dev", False)
-    assert abs(a["loss"] - c["loss"]) <= TOL * abs(a["loss"])
-    assert rel_err(c["iwes"], a["iwes"]) < TOL and rel_err(c["dtraj"], a["dtraj"]) < TOL
+    # float atomics: the l2 focus norm keeps the gradient smooth (with l1, sign(Sobel) of a ~0
+    # response flips with the summation order - see test_gpu_parity._assert_grad_close)
+    cfg2 = dict(cfg, focus_loss_norm="l2")
+    a2 = _run(cfg2, traj, times, ev, npos, "plain", True)
+    c = _run(cfg2, traj, times, ev, npos, "packed_dev", False)
+    assert abs(a2["loss"] - c["loss"]) <= TOL * abs(a2["loss"])
+    assert rel_err(c["iwes"], a2["iwes"]) < TOL and rel_err(c["dtraj"], a2["dtraj"]) < TOL
