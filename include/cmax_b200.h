@@ -132,6 +132,36 @@ int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const
                          int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
                          size_t workspace_bytes, void *stream);
 
+/* ---- phased calls: one window (or batch) whose EVENT ROWS are sharded over ranks -------------
+ * (second mode).  Every rank holds the same trajectories and its own slice of the
+ * event rows (any M per rank).  cmax_forward_accumulate builds the LUT and splats the local
+ * events into the raw-IWE section of the workspace; the caller sums that section over the ranks
+ * (ncclAllReduce / torch.distributed.all_reduce, in place); cmax_forward_finish runs the image
+ * stage on the summed IWE.  Backward: cmax_backward_accumulate leaves the local part of
+ * d loss / d LUT in the dLUT section (pass include_smooth = 1 on exactly one rank so that the
+ * smoothness gradient enters the sum once; ignored when deterministic), the caller all-reduces
+ * it, cmax_backward_finish gathers it into the trajectories.  Every rank ends with the same loss,
+ * IWEs and gradients as a single cmax_forward / cmax_backward over all the rows; in deterministic
+ * mode (int64 sections) bit for bit.
+ * cmax_workspace_section: byte offset / size of a reducible section inside the workspace and
+ * whether it holds int64 (deterministic) or float32 values. */
+enum { CMAX_SECTION_RAW_IWE = 0, CMAX_SECTION_DLUT = 1 };
+int cmax_workspace_section(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, int32_t which,
+                           size_t *offset_out, size_t *bytes_out, int32_t *is_int64_out);
+int cmax_forward_accumulate(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                            const float *events, int64_t B, int64_t M, int64_t n,
+                            int64_t num_pos_events, float *flow_lut_out, void *workspace,
+                            size_t workspace_bytes, void *stream);
+int cmax_forward_finish(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, float *iwes_out,
+                        float *losses_out, void *workspace, size_t workspace_bytes, void *stream);
+int cmax_backward_accumulate(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                             const float *events, int64_t B, int64_t M, int64_t n,
+                             int64_t num_pos_events, const float *grad_loss, int32_t include_smooth,
+                             void *workspace, size_t workspace_bytes, void *stream);
+int cmax_backward_finish(const CmaxConfig *cfg, const float *trajectories, int64_t B, int64_t M,
+                         int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
 /* Stand-alone imager, upstream EventImageConverter.create_iwe(events, method='bilinear_vote',
  * sigma, weight) (src/utils/event_image_converter.py:45-74,134-176,333-391).
  *   events [nb, M, row_stride] (first two columns y, x; row_stride >= 2 floats)

@@ -25,6 +25,8 @@ EXPORTS = (
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
     "cmax_last_worklist_count", "cmax_voxel_grid", "cmax_dense_flow",
     "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
+    "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
+    "cmax_backward_accumulate", "cmax_backward_finish",
 )
 
 
@@ -74,6 +76,21 @@ def load():
     lib.cmax_backward_packed.restype = c_int32
     lib.cmax_backward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
                                          P, P, P, c_size_t, P]
+    lib.cmax_workspace_section.restype = c_int32
+    lib.cmax_workspace_section.argtypes = [POINTER(CmaxConfig), c_int64, c_int64, c_int64, c_int32,
+                                           POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int32)]
+    lib.cmax_forward_accumulate.restype = c_int32
+    lib.cmax_forward_accumulate.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, c_int64,
+                                            c_int64, P, P, c_size_t, P]
+    lib.cmax_forward_finish.restype = c_int32
+    lib.cmax_forward_finish.argtypes = [POINTER(CmaxConfig), c_int64, c_int64, c_int64, P, P, P,
+                                        c_size_t, P]
+    lib.cmax_backward_accumulate.restype = c_int32
+    lib.cmax_backward_accumulate.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, c_int64,
+                                             c_int64, P, c_int32, P, c_size_t, P]
+    lib.cmax_backward_finish.restype = c_int32
+    lib.cmax_backward_finish.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, P, P,
+                                         c_size_t, P]
     lib.cmax_create_iwe.restype = c_int32
     lib.cmax_create_iwe.argtypes = [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_float, P,
                                     P, P, c_int32, P]
@@ -153,6 +170,17 @@ def pack_layout(cfg: CmaxConfig):
     out = (c_int32 * 4)()
     check(load().cmax_pack_layout(cfg, ctypes.byref(out)), "cmax_pack_layout")
     return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+
+
+SECTION_RAW_IWE, SECTION_DLUT = 0, 1
+
+
+def workspace_section(cfg: CmaxConfig, B: int, M: int, n: int, which: int):
+    """(byte offset, byte size, is_int64) of a reducible workspace section (event-sharded mode)."""
+    off, size, i64 = c_size_t(), c_size_t(), c_int32()
+    check(load().cmax_workspace_section(cfg, B, M, n, which, ctypes.byref(off), ctypes.byref(size),
+                                        ctypes.byref(i64)), "cmax_workspace_section")
+    return int(off.value), int(size.value), bool(i64.value)
 
 
 def stage_timing_read():

@@ -403,6 +403,105 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
     return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
 }
 
+// ---- phased entry points (event-sharded single-window mode) ------------------------
+int cmax_workspace_section(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, int32_t which,
+                           size_t *offset_out, size_t *bytes_out, int32_t *is_int64_out)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!offset_out || !bytes_out || !is_int64_out) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    const size_t npix = (size_t)(g.B * g.R * g.P) * g.H * g.W, nlut = (size_t)(g.S * g.q * g.R * 2);
+    *is_int64_out = g.det ? 1 : 0;
+    if (which == CMAX_SECTION_RAW_IWE) {
+        *offset_out = g.det ? L.raw_i64 : L.raw;
+        *bytes_out = npix * (g.det ? 8 : 4);
+    } else if (which == CMAX_SECTION_DLUT) {
+        *offset_out = g.det ? L.dlut_i64 : L.dlut;
+        *bytes_out = nlut * (g.det ? 8 : 4);
+    } else {
+        return CMAX_ERR_BAD_CONFIG;
+    }
+    return CMAX_OK;
+}
+
+int cmax_forward_accumulate(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                            const float *events, int64_t B, int64_t M, int64_t n,
+                            int64_t num_pos_events, float *flow_lut_out, void *workspace,
+                            size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!trajectories || !times || (!events && M > 0)) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(ws + L.header, 0, 1024, st);
+    if ((rc = launch_lut_forward(g, L, trajectories, ws, flow_lut_out, nullptr, nullptr, st))) return rc;
+    return launch_event_forward(g, L, events, times, ws, st, 1);
+}
+
+int cmax_forward_finish(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, float *iwes_out,
+                        float *losses_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!iwes_out || !losses_out) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_event_forward(g, L, nullptr, nullptr, ws, st, 2))) return rc;
+    if ((rc = launch_image_forward(g, L, ws, iwes_out, st))) return rc;
+    if ((rc = launch_smooth_forward(g, L, ws, st))) return rc;
+    return launch_finalize_losses(g, L, ws, losses_out, st);
+}
+
+int cmax_backward_accumulate(const CmaxConfig *cfg, const float *trajectories, const float *times,
+                             const float *events, int64_t B, int64_t M, int64_t n,
+                             int64_t num_pos_events, const float *grad_loss, int32_t include_smooth,
+                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!trajectories || !times || (!events && M > 0) || !grad_loss) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_image_backward(g, L, ws, st))) return rc;
+    if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
+    // float mode: the smoothness gradient sits in dLUT and must enter the sum over ranks once
+    if (!include_smooth && !g.det)
+        cudaMemsetAsync(ws + L.dlut, 0, sizeof(float) * g.S * g.q * g.R * 2, st);
+    return launch_event_backward(g, L, events, times, grad_loss, ws, st, 1);
+}
+
+int cmax_backward_finish(const CmaxConfig *cfg, const float *trajectories, int64_t B, int64_t M,
+                         int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
+                         size_t workspace_bytes, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, M, n, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if (!trajectories || !grad_loss || !dtraj_out) return CMAX_ERR_BAD_SHAPE;
+    const Layout L = make_layout(g);
+    if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < L.total)
+        return CMAX_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_event_backward(g, L, nullptr, nullptr, grad_loss, ws, st, 2))) return rc;
+    return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
+}
+
 static int pack_supported(const Geom &g)
 {
     if (g.nb > 256 || g.Hq > 4096 || g.Wq > 4096 || g.M > (int64_t)INT32_MAX) return CMAX_ERR_UNSUPPORTED;

@@ -69,9 +69,9 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
                         float *dtraj, cudaStream_t st);
 int launch_event_forward(const Geom &g, const Layout &L, const float *events, const float *times,
-                         char *ws, cudaStream_t st);
+                         char *ws, cudaStream_t st, int phase = 0);
 int launch_event_backward(const Geom &g, const Layout &L, const float *events, const float *times,
-                          const float *grad_loss, char *ws, cudaStream_t st);
+                          const float *grad_loss, char *ws, cudaStream_t st, int phase = 0);
 int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
                        int *scratch, long long *skipped, cudaStream_t st);
 int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
@@ -133,6 +133,13 @@ __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float 
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
+}
+
+// v * 2^32 as int64 (deterministic fixed point): the product is exact in float32 (power of two),
+// so this equals llrint((double)v * 2^32) bit for bit - without FP64 arithmetic.
+__device__ __forceinline__ long long to_fix(float v)
+{
+    return __float2ll_rn(__fmul_rn(v, 4294967296.0f));
 }
 
 // Python-style float floor division, the arithmetic of torch's `//` on float tensors

@@ -48,7 +48,7 @@ event_forward_kernel(const float *__restrict__ events, const float *__restrict__
             for (int k = 0; k < 4; ++k)
                 if (c.idx[k] >= 0)
                     atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + c.idx[k]),
-                              (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                              (unsigned long long)to_fix(v[k]));
         } else {
             // corners (y, x1) and (y, x1+1) are adjacent floats: one vector red when 8 B aligned
             // (plane base and row pitch are even, so alignment depends on x1 only)
@@ -119,8 +119,8 @@ event_backward_kernel(const float *__restrict__ events, const float *__restrict_
         const float gx = w * (oy * (d01 - d00) + c.fy * (d11 - d10));
         if (DET) {
             unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
-            atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
-            atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
+            atomicAdd(dst, (unsigned long long)to_fix(gy));
+            atomicAdd(dst + 1, (unsigned long long)to_fix(gx));
         } else {
             red_add_f32x2(dlut + (cell * g.R + r) * 2, coef * gy, coef * gx);
         }
@@ -173,7 +173,7 @@ splat_kernel(const float *__restrict__ events, const float *__restrict__ weight,
         if (c.idx[k] >= 0) {
             if (MODE == 1)
                 atomicAdd(reinterpret_cast<unsigned long long *>(out_i64 + base + c.idx[k]),
-                          (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                          (unsigned long long)to_fix(v[k]));
             else
                 atomicAdd(out + base + c.idx[k], v[k]);
         }
@@ -205,14 +205,17 @@ int launch_fix_to_float(const long long *in, float *out, int64_t count, cudaStre
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// phase 0: everything; 1: accumulate only (leaves the int64 sums un-converted when deterministic);
+// 2: only the deterministic conversion.  Phases 1 / 2 bracket the all-reduce of the event-sharded mode.
 int launch_event_forward(const Geom &g, const Layout &L, const float *events, const float *times,
-                         char *ws, cudaStream_t st)
+                         char *ws, cudaStream_t st, int phase)
 {
     const int64_t count = g.B * g.R * g.P * (int64_t)g.H * g.W;
     float *raw = reinterpret_cast<float *>(ws + L.raw);
     long long *raw_i64 = reinterpret_cast<long long *>(ws + L.raw_i64);
     long long *status = reinterpret_cast<Header *>(ws + L.header)->status;
     const float *lut = reinterpret_cast<const float *>(ws + L.lut);
+    if (phase == 2) return g.det ? launch_fix_to_float(raw_i64, raw, count, st) : CMAX_OK;
     StageScope sc(ST_EVENT_FWD, st);
     count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
     if (g.det)
@@ -226,12 +229,12 @@ int launch_event_forward(const Geom &g, const Layout &L, const float *events, co
         else
             event_forward_kernel<false><<<grid, 256, 0, st>>>(events, times, g, lut, raw, raw_i64, status);
     }
-    if (g.det) return launch_fix_to_float(raw_i64, raw, count, st);
+    if (g.det && phase == 0) return launch_fix_to_float(raw_i64, raw, count, st);
     return check_launch();
 }
 
 int launch_event_backward(const Geom &g, const Layout &L, const float *events, const float *times,
-                          const float *grad_loss, char *ws, cudaStream_t st)
+                          const float *grad_loss, char *ws, cudaStream_t st, int phase)
 {
     const int64_t count = g.S * g.q * g.R * 2;
     const Header *hdr = reinterpret_cast<const Header *>(ws + L.header);
@@ -239,6 +242,7 @@ int launch_event_backward(const Geom &g, const Layout &L, const float *events, c
     const float *dimg = reinterpret_cast<const float *>(ws + L.dimg);
     float *dlut = reinterpret_cast<float *>(ws + L.dlut);
     long long *dlut_i64 = reinterpret_cast<long long *>(ws + L.dlut_i64);
+    if (phase == 2) return g.det ? launch_dlut_finalize(g, L, grad_loss, ws, st) : CMAX_OK;
     StageScope sc(ST_EVENT_BWD, st);
     count_launch((g.M > 0 ? 1 : 0) + (g.det ? 1 : 0));
     if (g.det) cudaMemsetAsync(dlut_i64, 0, sizeof(long long) * count, st);
@@ -251,7 +255,7 @@ int launch_event_backward(const Geom &g, const Layout &L, const float *events, c
             event_backward_kernel<false><<<grid, 256, 0, st>>>(events, times, g, lut, dimg, hdr,
                                                                 grad_loss, dlut, dlut_i64);
     }
-    if (g.det) return launch_dlut_finalize(g, L, grad_loss, ws, st);
+    if (g.det && phase == 0) return launch_dlut_finalize(g, L, grad_loss, ws, st);
     return check_launch();
 }
 

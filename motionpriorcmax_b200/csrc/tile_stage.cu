@@ -13,9 +13,12 @@
 //
 // Events of one (tile, group) segment are warped by the flows of one small LUT block, so their
 // votes land in a compact neighbourhood of the tile.  One CTA per segment (slice):
-//   forward   votes go into a 64 x 64 pixel window in SHARED memory (red.shared.add.f32, or u64
-//             fixed point when deterministic) whose origin follows the flow range of the tile's
-//             LUT block; one flush of the non-zero quads with red.global.add.v4.f32.
+//   forward   votes go into a 64 x 64 pixel window in SHARED memory whose origin follows the flow
+//             range of the tile's LUT block; one flush of the non-zero quads with
+//             red.global.add.v4.f32 (u64 atomics when deterministic).  The window accumulates in
+//             2^-32 FIXED POINT as (low, high) 32-bit words with native ATOMS.ADD and an explicit
+//             carry: float and 64-bit shared-memory atomics compile to compare-and-swap spin
+//             loops on sm_100 (measured 2x slower), integer 32-bit adds are native and exact.
 //             Votes that leave the window fall back to the global reds of event_stage.cu, so any
 //             flow magnitude stays exact.
 //   backward  the same window of dL/dIWE is staged in shared memory, the four gathers are
@@ -40,6 +43,22 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p)
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
+}
+
+// 64-bit fixed-point add into a (low, high) pair of shared-memory words: two native 32-bit
+// atomics; the carry out of the low word is recovered from the value the first add returns.
+__device__ __forceinline__ void smem_add_fix(unsigned *lo, unsigned *hi, long long x)
+{
+    if (x == 0) return;
+    const unsigned xl = (unsigned)x, xh = (unsigned)((unsigned long long)x >> 32);
+    const unsigned old = atomicAdd(lo, xl);
+    const unsigned h = xh + ((old + xl) < old ? 1u : 0u);
+    if (h) atomicAdd(hi, h);
+}
+
+__device__ __forceinline__ long long smem_get_fix(const unsigned *lo, const unsigned *hi)
+{
+    return (long long)(((unsigned long long)*hi << 32) | (unsigned long long)*lo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,9 +343,9 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
                           const float *__restrict__ lut, float *__restrict__ raw,
                           long long *__restrict__ raw_i64)
 {
-    using Acc = typename std::conditional<DET, unsigned long long, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Acc *s_win = reinterpret_cast<Acc *>(smem_raw);
+    unsigned *s_lo = reinterpret_cast<unsigned *>(smem_raw);          // [kWin * kWin] low words
+    unsigned *s_hi = s_lo + kWin * kWin;                              // [kWin * kWin] high words
     __shared__ int s_org[2];
 
     const Seg sg = cta_segment(g, seg_start, split);
@@ -341,7 +360,8 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
     for (int r = 0; r < g.R; ++r) {
         int oy = 0, ox = 0;
         if (use_win) {
-            for (int i = tid; i < kWin * kWin; i += kTileThreads) s_win[i] = (Acc)0;
+            for (int i = tid; i < kWin * kWin / 2; i += kTileThreads)
+                reinterpret_cast<uint4 *>(s_lo)[i] = make_uint4(0u, 0u, 0u, 0u);       // both arrays
             window_origin(g, lut, b, sg, r, s_org, &oy, &ox);       // ends with a barrier
         }
         // window entirely inside the image: every corner that is in the window is in bounds
@@ -368,15 +388,11 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
             v[3] = __fmul_rn(__fmul_rn(fy, fx), w);
             const bool in_win = y1 >= wy0 && y1 < wy1 && x1 >= wx0 && x1 < wx1;
             if (in_win && interior) {
-                Acc *p = s_win + ((int)y1 - oy) * kWin + ((int)x1 - ox);
+                const int p = ((int)y1 - oy) * kWin + ((int)x1 - ox);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    Acc *q = p + (k & 1) * kWin + (k >> 1);
-                    if (DET)
-                        atomicAdd(reinterpret_cast<unsigned long long *>(q),
-                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
-                    else
-                        atomicAdd(reinterpret_cast<float *>(q), v[k]);
+                    const int q = p + (k & 1) * kWin + (k >> 1);
+                    smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
                 }
                 continue;
             }
@@ -384,16 +400,12 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
             if (!c.finite) continue;
             const bool ok[4] = {c.y0ok && c.x0ok, c.y1ok && c.x0ok, c.y0ok && c.x1ok, c.y1ok && c.x1ok};
             if (in_win) {
-                Acc *p = s_win + (c.y - oy) * kWin + (c.x - ox);
+                const int p = (c.y - oy) * kWin + (c.x - ox);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (!ok[k]) continue;
-                    Acc *q = p + (k & 1) * kWin + (k >> 1);
-                    if (DET)
-                        atomicAdd(reinterpret_cast<unsigned long long *>(q),
-                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
-                    else
-                        atomicAdd(reinterpret_cast<float *>(q), v[k]);
+                    const int q = p + (k & 1) * kWin + (k >> 1);
+                    smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
                 }
             } else {
 #pragma unroll
@@ -402,7 +414,7 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
                     const int64_t idx = base + (int64_t)(c.y + (k & 1)) * g.W + c.x + (k >> 1);
                     if (DET)
                         atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + idx),
-                                  (unsigned long long)__double2ll_rn((double)v[k] * kFixScale));
+                                  (unsigned long long)to_fix(v[k]));
                     else
                         atomicAdd(raw + idx, v[k]);
                 }
@@ -413,23 +425,28 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
         // flush the non-zero part of the window
         if (DET) {
             for (int i = tid; i < kWin * kWin; i += kTileThreads) {
-                const unsigned long long v = reinterpret_cast<unsigned long long *>(s_win)[i];
+                const long long v = smem_get_fix(s_lo + i, s_hi + i);
                 const int gy = oy + i / kWin, gx = ox + i % kWin;
-                if (v != 0ull && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + (int64_t)gy * g.W + gx), v);
+                if (v != 0 && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(raw_i64 + base + (int64_t)gy * g.W + gx),
+                              (unsigned long long)v);
             }
         } else {
-            const float4 *w4 = reinterpret_cast<const float4 *>(s_win);
             for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
-                const float4 v = w4[i];
-                if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
+                const uint4 l4 = reinterpret_cast<const uint4 *>(s_lo)[i];
+                const uint4 h4 = reinterpret_cast<const uint4 *>(s_hi)[i];
+                if ((l4.x | l4.y | l4.z | l4.w | h4.x | h4.y | h4.z | h4.w) == 0u) continue;
                 const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));
                 if (gy < 0 || gy >= g.H) continue;
+                const unsigned lo[4] = {l4.x, l4.y, l4.z, l4.w}, hi[4] = {h4.x, h4.y, h4.z, h4.w};
+                float vv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)          // one rounding of the exact tile sum
+                    vv[k] = __ll2float_rn(smem_get_fix(lo + k, hi + k)) * (1.0f / 4294967296.0f);
                 const int64_t idx = base + (int64_t)gy * g.W + gx;
                 if (gx >= 0 && gx + 3 < g.W && (idx & 3) == 0) {
-                    red_add_f32x4(raw + idx, v.x, v.y, v.z, v.w);
+                    red_add_f32x4(raw + idx, vv[0], vv[1], vv[2], vv[3]);
                 } else {
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (vv[k] != 0.0f && gx + k >= 0 && gx + k < g.W) atomicAdd(raw + idx + k, vv[k]);
@@ -451,10 +468,10 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
                            const Header *__restrict__ hdr, const float *__restrict__ grad_loss,
                            float *__restrict__ dlut, long long *__restrict__ dlut_i64)
 {
-    using Acc = typename std::conditional<DET, unsigned long long, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_D = reinterpret_cast<float *>(smem_raw);                       // [kWin * kWin]
-    Acc *s_acc = reinterpret_cast<Acc *>(smem_raw + sizeof(float) * kWin * kWin);   // [nb, ct, ct, 2]
+    // dLUT block of the tile, [nb, ct, ct, 2] in 2^-32 fixed point: low words, then high words
+    unsigned *s_alo = reinterpret_cast<unsigned *>(smem_raw + sizeof(float) * kWin * kWin);
     __shared__ int s_org[2];
 
     const Seg sg = cta_segment(g, seg_start, split);
@@ -466,6 +483,7 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
     const bool use_win = sg.e - sg.a >= 64;
     const bool use_acc = use_win && smem_acc;
     const int cc = g.ct * g.ct, nacc = cc * g.nb;
+    unsigned *s_ahi = s_alo + 2 * nacc;
     float coef = 1.0f;
     if (!DET) {
         const float val = hdr->val;
@@ -479,7 +497,7 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
         int oy = 0, ox = 0;
         if (use_win) {
             if (use_acc)
-                for (int i = tid; i < nacc * 2; i += kTileThreads) s_acc[i] = (Acc)0;
+                for (int i = tid; i < nacc * 4; i += kTileThreads) s_alo[i] = 0u;       // both arrays
             window_origin(g, lut, b, sg, r, s_org, &oy, &ox);
             // stage dL/dIWE of the window (zero outside the image)
             if ((g.W & 3) == 0 && ((((b * g.R + r) * g.P + sg.grp) * HW) & 3) == 0) {
@@ -539,20 +557,13 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
             const float gx = w * (oyw * (d01 - d00) + fy * (d11 - d10));
             const int cy = pe.iy - sg.ty * g.ct, cx = pe.ix - sg.tx * g.ct;
             if (use_acc && (unsigned)cy < (unsigned)g.ct && (unsigned)cx < (unsigned)g.ct) {
-                Acc *q = s_acc + 2 * ((pe.bin * g.ct + cy) * g.ct + cx);
-                if (DET) {
-                    atomicAdd(reinterpret_cast<unsigned long long *>(q),
-                              (unsigned long long)__double2ll_rn((double)gy * kFixScale));
-                    atomicAdd(reinterpret_cast<unsigned long long *>(q) + 1,
-                              (unsigned long long)__double2ll_rn((double)gx * kFixScale));
-                } else {
-                    atomicAdd(reinterpret_cast<float *>(q), coef * gy);
-                    atomicAdd(reinterpret_cast<float *>(q) + 1, coef * gx);
-                }
+                const int q = 2 * ((pe.bin * g.ct + cy) * g.ct + cx);
+                smem_add_fix(s_alo + q, s_ahi + q, to_fix(gy));
+                smem_add_fix(s_alo + q + 1, s_ahi + q + 1, to_fix(gx));
             } else if (DET) {
                 unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + ((int64_t)cell * g.R + r) * 2;
-                atomicAdd(dst, (unsigned long long)__double2ll_rn((double)gy * kFixScale));
-                atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)gx * kFixScale));
+                atomicAdd(dst, (unsigned long long)to_fix(gy));
+                atomicAdd(dst + 1, (unsigned long long)to_fix(gx));
             } else {
                 red_add_f32x2(dlut + ((int64_t)cell * g.R + r) * 2, coef * gy, coef * gx);
             }
@@ -565,16 +576,17 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
                 const int iy = sg.ty * g.ct + c2 / g.ct, ix = sg.tx * g.ct + c2 % g.ct;
                 if (iy >= g.Hq || ix >= g.Wq) continue;
                 const int64_t cell = ((b * g.nb + bin) * g.Hq + iy) * g.Wq + ix;
+                const long long a0 = smem_get_fix(s_alo + 2 * i, s_ahi + 2 * i);
+                const long long a1 = smem_get_fix(s_alo + 2 * i + 1, s_ahi + 2 * i + 1);
+                if (a0 == 0 && a1 == 0) continue;
                 if (DET) {
-                    const unsigned long long a0 = reinterpret_cast<unsigned long long *>(s_acc)[2 * i];
-                    const unsigned long long a1 = reinterpret_cast<unsigned long long *>(s_acc)[2 * i + 1];
                     unsigned long long *dst = reinterpret_cast<unsigned long long *>(dlut_i64) + (cell * g.R + r) * 2;
-                    if (a0 != 0ull) atomicAdd(dst, a0);
-                    if (a1 != 0ull) atomicAdd(dst + 1, a1);
+                    if (a0 != 0) atomicAdd(dst, (unsigned long long)a0);
+                    if (a1 != 0) atomicAdd(dst + 1, (unsigned long long)a1);
                 } else {
-                    const float a0 = reinterpret_cast<float *>(s_acc)[2 * i];
-                    const float a1 = reinterpret_cast<float *>(s_acc)[2 * i + 1];
-                    if (a0 != 0.0f || a1 != 0.0f) red_add_f32x2(dlut + (cell * g.R + r) * 2, a0, a1);
+                    red_add_f32x2(dlut + (cell * g.R + r) * 2,
+                                  coef * (__ll2float_rn(a0) * (1.0f / 4294967296.0f)),
+                                  coef * (__ll2float_rn(a1) * (1.0f / 4294967296.0f)));
                 }
             }
         }
@@ -618,15 +630,13 @@ int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *re
     if (g.M > 0) {
         const int split = pick_split(g);
         dim3 grid((unsigned)(g.nt * split), (unsigned)g.P, (unsigned)g.B);
-        if (g.det) {
-            const size_t sm = sizeof(unsigned long long) * kWin * kWin;
+        const size_t sm = 2 * sizeof(unsigned) * kWin * kWin;
+        if (g.det)
             event_forward_tile_kernel<true><<<grid, kTileThreads, sm, st>>>(records, seg_start, times, g,
                                                                             split, lut, raw, raw_i64);
-        } else {
-            const size_t sm = sizeof(float) * kWin * kWin;
+        else
             event_forward_tile_kernel<false><<<grid, kTileThreads, sm, st>>>(records, seg_start, times, g,
                                                                              split, lut, raw, raw_i64);
-        }
     }
     if (g.det) return launch_fix_to_float(raw_i64, raw, count, st);
     return check_launch();
@@ -648,7 +658,7 @@ int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *r
     if (g.M > 0) {
         const int split = pick_split(g);
         dim3 grid((unsigned)(g.nt * split), (unsigned)g.P, (unsigned)g.B);
-        const size_t acc = (size_t)g.ct * g.ct * g.nb * 2 * (g.det ? sizeof(unsigned long long) : sizeof(float));
+        const size_t acc = (size_t)g.ct * g.ct * g.nb * 2 * 2 * sizeof(unsigned);
         const int smem_acc = acc <= (size_t)kMaxSmemAcc ? 1 : 0;
         const size_t sm = sizeof(float) * kWin * kWin + (smem_acc ? acc : 0);
         int rc;

@@ -212,3 +212,10 @@ class FocusLoss(base.TrajectoryLossBase):
         if return_flow_lut:
             misc_metadata['flow_lut'] = out[3]
         return loss, log_metadata, misc_metadata
+
+    def calc_event_sharded(self, trajectories, times, batch, group=None):
+        """`calc` for windows whose event rows are sharded over the ranks of `group` (SURVEY 8e,
+        second mode): `batch['events']` = this rank's rows; two in-place all-reduces (raw IWE,
+        dLUT) make loss, IWEs and gradients identical on every rank.  See losses/sharded.py."""
+        from . import sharded
+        return sharded.calc_event_sharded(self, trajectories, times, batch, group=group)

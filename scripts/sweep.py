@@ -5,7 +5,7 @@ Windows are generated on the device (uniform events, time sorted, loader layout)
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from motionpriorcmax_b200 import synthetic, trajectories as tj, cabi
+from motionpriorcmax_b200 import synthetic, trajectories as tj, cabi, io as cio
 from motionpriorcmax_b200.losses import LossFactory
 
 
@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--batch", default="1,14")
     ap.add_argument("--events", default="1e5,3e5,1e6,3e6,1e7,3e7,5e7")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--layouts", default="plain,packed", help="plain = upstream [B,M,6]; packed = io.PackedEvents")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = dict(synthetic.DSEC_LOSS_CONFIG)
@@ -51,26 +52,48 @@ def main():
                 continue
             ev, npos = device_batch(B, M, H, W, cfg["num_bins"], dev, seed=B * 1000 + 7)
 
-            def step():
-                cg.grad = None
-                traj = tj.calculate_trajectories_at_t(cg, times, 4, 1, "polynomial")
-                loss, _, _ = L.calc(traj, times, {"events": ev, "num_pos_events": npos})
-                loss.backward()
-            for _ in range(3):
-                step()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(a.steps):
-                step()
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.steps
-            n_t, n, Q = 16, 19200, 15 * 19200
-            bytes_alg = 48 * B * M + 20 * B * 2 * H * W + 24 * B * Q + 16 * B * n_t * n
-            rows.append({"B": B, "events_per_window": M, "ms_per_step": ms, "events_per_s": B * M / ms * 1e3,
-                         "algorithmic_GB": bytes_alg / 1e9, "achieved_GBps": bytes_alg / ms / 1e6,
-                         "hbm_frac": bytes_alg / ms / 1e6 / peak})
-            print(json.dumps(rows[-1]), file=sys.stderr)
+            for layout in a.layouts.split(","):
+                batch = {"events": ev, "num_pos_events": npos}
+                pack_ms = None
+                if layout == "packed":
+                    pk = cio.pack_events(ev, npos, L)
+                    torch.cuda.synchronize()
+                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    p0.record()
+                    pk = cio.pack_events(ev, npos, L)
+                    p1.record(); torch.cuda.synchronize()
+                    pack_ms = p0.elapsed_time(p1)
+                    batch = {"events": pk}
+
+                def step():
+                    cg.grad = None
+                    traj = tj.calculate_trajectories_at_t(cg, times, 4, 1, "polynomial")
+                    loss, _, _ = L.calc(traj, times, batch)
+                    loss.backward()
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cabi.load().cmax_stage_timing_enable(1)
+                e0.record()
+                for _ in range(a.steps):
+                    step()
+                e1.record(); torch.cuda.synchronize()
+                st = cabi.stage_timing_read()
+                cabi.load().cmax_stage_timing_enable(0)
+                ms = e0.elapsed_time(e1) / a.steps
+                n_t, n, Q = 16, 19200, 15 * 19200
+                ev_bytes = (32 if layout == "packed" else 48) * B * M      # records are 16 B, read twice
+                bytes_alg = ev_bytes + 20 * B * 2 * H * W + 24 * B * Q + 16 * B * n_t * n
+                rows.append({"B": B, "events_per_window": M, "layout": layout, "ms_per_step": ms,
+                             "events_per_s": B * M / ms * 1e3, "algorithmic_GB": bytes_alg / 1e9,
+                             "achieved_GBps": bytes_alg / ms / 1e6, "hbm_frac": bytes_alg / ms / 1e6 / peak,
+                             "event_forward_ms": st["event_forward"][0] / max(st["event_forward"][1], 1),
+                             "event_backward_ms": st["event_backward"][0] / max(st["event_backward"][1], 1),
+                             "device_pack_ms": pack_ms})
+                print(json.dumps(rows[-1]), file=sys.stderr)
+                batch = None
+                pk = None
             del ev
             torch.cuda.empty_cache()
     print(json.dumps({"peak_GBps": peak, "rows": rows}, indent=1))
