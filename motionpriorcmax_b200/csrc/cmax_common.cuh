@@ -142,6 +142,15 @@ __device__ __forceinline__ long long to_fix(float v)
     return __float2ll_rn(__fmul_rn(v, 4294967296.0f));
 }
 
+// sqrt.approx (MUFU, ~1 ulp): ONLY for search bounds that carry their own safety margin - never
+// for a value the reference computes.  The IEEE sqrtf costs ~15 instructions under -prec-sqrt.
+__device__ __forceinline__ float approx_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Python-style float floor division, the arithmetic of torch's `//` on float tensors
 // (c10 div_floor_floating) used by focus.py:186-187.
 __device__ __forceinline__ float floordiv_f32(float a, float b)

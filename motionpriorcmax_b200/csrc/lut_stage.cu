@@ -391,7 +391,7 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
             dym = fmaxf(dym, 0.0f) * (1.0f - 1e-5f);
             const float rem = L1D ? hi - dym : hi - dym * dym;
             if (!(rem > 0.0f)) return false;
-            const float hw = (L1D ? rem : sqrtf(rem)) * (1.0f + 1e-5f) + 1e-6f;
+            const float hw = (L1D ? rem : approx_sqrt(rem)) * (1.0f + 1e-5f) + 1e-6f;
             const float cl = fminf(fmaxf(floorf((qx - hw) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
             const float ch = fminf(fmaxf(floorf((qx + hw) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
             const int c0 = max((int)cl - wx0, c0w), c1 = min((int)ch - wx0 + 1, c1w);
@@ -843,7 +843,7 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
     const int slab = b * g.nb + bin;
     const float2 p = slab_points(traj, g, slab)[j];
     const float tm = __uint_as_float(__ldg(tau_max + slab));
-    float rho_g = L1D ? tm : sqrtf(tm);
+    float rho_g = L1D ? tm : approx_sqrt(tm);
     rho_g = rho_g * 1.0001f + 1e-3f;
     float2 nxt = make_float2(0.f, 0.f);
     float2 binr[RT ? RT : kMaxTref];
@@ -863,7 +863,10 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
         const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
         const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
         const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
-        float rho = 0.0f;
+        // a tile matters when its rectangle is closer to p than its own reach; compared on the
+        // tau scale itself (squared distance for l2) with a relative + absolute margin, so the
+        // loop needs no square root - one at the end gives the search radius
+        float tbest = -1.0f;
         for (int ty = ty0; ty <= ty1; ++ty) {
             const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
             const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
@@ -873,11 +876,11 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
                 const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
                 const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
                 const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
-                const float reach = (L1D ? tmt : sqrtf(tmt)) * 1.0001f + 1e-3f;
-                const float gap = L1D ? ddy + ddx : sqrtf(ddy * ddy + ddx * ddx);
-                if (gap <= reach) rho = fmaxf(rho, reach);
+                const float gap = L1D ? ddy + ddx : ddy * ddy + ddx * ddx;
+                if (gap <= tmt * 1.001f + 1e-2f) tbest = fmaxf(tbest, tmt);
             }
         }
+        const float rho = tbest < 0.0f ? 0.0f : (L1D ? tbest : approx_sqrt(tbest)) * 1.0001f + 1e-3f;
         const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
         const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
         const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
@@ -887,7 +890,7 @@ lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restr
             const float dy = __fsub_rn(qy, p.x);
             const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
             // clip the row to the reach disc (l1: diamond); conservative by one cell
-            const float hx = L1D ? rho - fabsf(dy) : sqrtf(fmaxf(rho * rho - dy * dy, 0.0f));
+            const float hx = L1D ? rho - fabsf(dy) : approx_sqrt(fmaxf(rho * rho - dy * dy, 0.0f)) * 1.0001f + 1e-3f;
             const int jx0 = max(ix0, (int)floorf((p.y - hx - g.off) * inv_s));
             const int jx1 = min(ix1, (int)ceilf((p.y + hx - g.off) * inv_s));
             const int nx = jx1 - jx0 + 1;
