@@ -60,7 +60,12 @@ typedef struct CmaxConfig {
                                          (run-to-run bit-identical); 0: float32 atomics          */
     int32_t focus_functional;         /* CMAX_FOCUS_GRADIENT_MAGNITUDE (what upstream calc hard-codes,
                                          focus.py:90) | CMAX_FOCUS_VARIANCE (loss.py:14-16)       */
-    int32_t reserved[2];
+    int32_t backward_follows;         /* training hint: 1 = cmax_backward will be called on this
+                                         workspace.  cmax_forward then emits dL/dIWE from the same pass
+                                         that blurs / scores the IWE (one kernel instead of two; the
+                                         matching cmax_backward, given the SAME config, skips that
+                                         stage).  Results are unchanged.  0 = forward only / unknown. */
+    int32_t reserved[1];
 } CmaxConfig;
 
 int cmax_abi_version(void);

@@ -37,7 +37,7 @@ class CmaxConfig(Structure):
         ("dist_norm", c_int32), ("scale_iwe_by_dt", c_int32), ("mask_image_border", c_int32),
         ("polarity_aware_batching", c_int32), ("interpolation_scheme", c_int32),
         ("smooth_type", c_int32), ("smooth_weight", c_float), ("deterministic", c_int32),
-        ("focus_functional", c_int32), ("reserved", c_int32 * 2),
+        ("focus_functional", c_int32), ("backward_follows", c_int32), ("reserved", c_int32 * 1),
     ]
 
 
@@ -162,6 +162,13 @@ def make_config(image_shape, num_tref, num_bins, num_knn, smooth_weight, lut_sup
     if focus_loss_type not in FOCUS:
         raise ValueError(f"focus_loss_type={focus_loss_type!r} not in {sorted(FOCUS)}")
     c.focus_functional = FOCUS[focus_loss_type]
+    return c
+
+
+def with_backward_hint(cfg: CmaxConfig) -> CmaxConfig:
+    """Copy of `cfg` with `backward_follows = 1` (the forward fuses the image-stage adjoint)."""
+    c = CmaxConfig.from_buffer_copy(cfg)
+    c.backward_follows = 1
     return c
 
 

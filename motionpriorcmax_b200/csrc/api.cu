@@ -121,6 +121,7 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     g->smooth_next = c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT;
     g->det = c->deterministic != 0;
     g->variance = c->focus_functional == CMAX_FOCUS_VARIANCE;
+    g->fuse_image = (c->backward_follows != 0) && !g->variance;
     g->smooth_w = c->smooth_weight;
     g->B = B;
     g->M = M;
@@ -377,7 +378,8 @@ int cmax_forward(const CmaxConfig *cfg, const float *trajectories, const float *
     cudaMemsetAsync(ws + L.header, 0, 1024, st);
     if ((rc = launch_lut_forward(g, L, trajectories, ws, flow_lut_out, nullptr, nullptr, st))) return rc;
     if ((rc = launch_event_forward(g, L, events, times, ws, st))) return rc;
-    if ((rc = launch_image_forward(g, L, ws, iwes_out, st))) return rc;
+    if ((rc = g.fuse_image ? launch_image_forward_backward(g, L, ws, iwes_out, st)
+                           : launch_image_forward(g, L, ws, iwes_out, st))) return rc;
     if ((rc = launch_smooth_forward(g, L, ws, st))) return rc;
     return launch_finalize_losses(g, L, ws, losses_out, st);
 }
@@ -397,7 +399,7 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
         return CMAX_ERR_WORKSPACE;
     char *ws = static_cast<char *>(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = launch_image_backward(g, L, ws, st))) return rc;
+    if (!g.fuse_image && (rc = launch_image_backward(g, L, ws, st))) return rc;   // else done by the forward
     if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
     if ((rc = launch_event_backward(g, L, events, times, grad_loss, ws, st))) return rc;
     return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
@@ -559,7 +561,8 @@ int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const 
     if ((rc = launch_lut_forward(g, L, trajectories, ws, flow_lut_out, nullptr, nullptr, st))) return rc;
     if ((rc = launch_event_forward_packed(g, L, reinterpret_cast<const float4 *>(records), seg_start,
                                           times, ws, st))) return rc;
-    if ((rc = launch_image_forward(g, L, ws, iwes_out, st))) return rc;
+    if ((rc = g.fuse_image ? launch_image_forward_backward(g, L, ws, iwes_out, st)
+                           : launch_image_forward(g, L, ws, iwes_out, st))) return rc;
     if ((rc = launch_smooth_forward(g, L, ws, st))) return rc;
     return launch_finalize_losses(g, L, ws, losses_out, st);
 }
@@ -580,7 +583,7 @@ int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const
         return CMAX_ERR_WORKSPACE;
     char *ws = static_cast<char *>(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = launch_image_backward(g, L, ws, st))) return rc;
+    if (!g.fuse_image && (rc = launch_image_backward(g, L, ws, st))) return rc;   // else done by the forward
     if ((rc = launch_smooth_backward(g, L, grad_loss, ws, st))) return rc;
     if ((rc = launch_event_backward_packed(g, L, reinterpret_cast<const float4 *>(records), seg_start,
                                            times, grad_loss, ws, st))) return rc;

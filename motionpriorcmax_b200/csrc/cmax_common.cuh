@@ -36,6 +36,7 @@ struct Geom {                 // derived sizes, passed by value to kernels
     int r0;                   // initial search radius in cells (heap path)
     int r_fast;               // window radius of the staged fast path
     int l1dist, l2focus, scale_dt, mask_border, pab, iwd, smooth_next, det, variance;
+    int fuse_image;           // training hint: the forward also produces dL/dIWE (image stage fused)
     float smooth_w;
     int64_t B, M, n, S;       // S = B * nb
     int64_t npos;
@@ -84,6 +85,8 @@ int launch_dlut_finalize(const Geom &g, const Layout &L, const float *grad_loss,
                          cudaStream_t st);
 int launch_image_forward(const Geom &g, const Layout &L, char *ws, float *iwes_out, cudaStream_t st);
 int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
+int launch_image_forward_backward(const Geom &g, const Layout &L, char *ws, float *iwes_out,
+                                  cudaStream_t st);
 int launch_smooth_forward(const Geom &g, const Layout &L, char *ws, cudaStream_t st);
 int launch_smooth_backward(const Geom &g, const Layout &L, const float *grad_loss, char *ws,
                            cudaStream_t st);

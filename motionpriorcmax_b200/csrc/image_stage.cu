@@ -116,10 +116,17 @@ blur_kernel(const float *__restrict__ raw, float *__restrict__ out, int H, int W
 
 // ---- backward: unscaled dL/dIWE_raw ------------------------------------------------------------
 // D' = blur^T( Sobel_x^T u + Sobel_y^T v ),  (u, v) = (sign dx, sign dy)  [l1]  or (2dx, 2dy) [l2]
+// FWD = true: the same pass also emits what image_forward_kernel produces (blurred IWE, per-CTA
+// partial focus sum) - D' does not depend on the loss value, so when a backward is known to
+// follow (training) one kernel serves both directions and the raw IWE is read once.
+template <bool FWD>
 __global__ void __launch_bounds__(256)
 image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, int H, int W,
-                      Gauss3 gk, int l2, int variance, const double *__restrict__ plane_stats)
+                      Gauss3 gk, int l2, int variance, const double *__restrict__ plane_stats,
+                      float *__restrict__ blurred_out, double *__restrict__ partials, int n_blocks)
 {
+    __shared__ double s_red[FWD ? 32 : 1];
+    double facc = 0.0;
     __shared__ float s_raw[T + 8][T + 8 + 1];
     __shared__ float s_blur[T + 6][T + 6 + 1];
     __shared__ float s_u[T + 4][T + 4 + 1];
@@ -180,9 +187,21 @@ image_backward_kernel(const float *__restrict__ raw, float *__restrict__ dimg, i
                 u = dx > 0.0f ? 1.0f : (dx < 0.0f ? -1.0f : 0.0f);     // torch sign(0) = 0
                 v = dy > 0.0f ? 1.0f : (dy < 0.0f ? -1.0f : 0.0f);
             }
+            if (FWD && ly >= 2 && ly < T + 2 && lx >= 2 && lx < T + 2) {      // the tile's own pixels
+                facc += l2 ? (double)(dx * dx + dy * dy) : (double)(fabsf(dx) + fabsf(dy));
+                blurred_out[plane * (int64_t)H * W + (int64_t)yy * W + xx] = s_blur[ly + 1][lx + 1];
+            }
         }
         s_u[ly][lx] = u;
         s_v[ly][lx] = v;
+    }
+    if (FWD) {
+        facc = block_sum(facc, s_red);                      // contains the barriers
+        if (tid == 0) {
+            const int64_t idx = (plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            partials[idx] = facc;
+            partials[n_blocks + idx] = 0.0;
+        }
     }
     __syncthreads();
     // G = Sobel_x^T u + Sobel_y^T v on tile + halo 1 (positions outside the image are unused)
@@ -438,9 +457,26 @@ int launch_image_backward(const Geom &g, const Layout &L, char *ws, cudaStream_t
     dim3 grid((g.W + T - 1) / T, (g.H + T - 1) / T, (unsigned)planes);
     StageScope sc(ST_IMAGE_BWD, st);
     count_launch();
-    image_backward_kernel<<<grid, dim3(32, 8), 0, st>>>(
+    image_backward_kernel<false><<<grid, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const float *>(ws + L.raw), reinterpret_cast<float *>(ws + L.dimg), g.H,
-        g.W, gauss3(1.0f), g.l2focus, g.variance, reinterpret_cast<const double *>(ws + L.plane_stats));
+        g.W, gauss3(1.0f), g.l2focus, g.variance, reinterpret_cast<const double *>(ws + L.plane_stats),
+        nullptr, nullptr, 0);
+    return check_launch();
+}
+
+// forward and the focus part of the backward in one pass (training hint; gradient-magnitude
+// functional only - the variance functional needs the plane means first)
+int launch_image_forward_backward(const Geom &g, const Layout &L, char *ws, float *iwes_out,
+                                  cudaStream_t st)
+{
+    const int64_t planes = g.B * g.R * g.P;
+    dim3 grid((g.W + T - 1) / T, (g.H + T - 1) / T, (unsigned)planes);
+    StageScope sc(ST_IMAGE_FWD, st);
+    count_launch();
+    image_backward_kernel<true><<<grid, dim3(32, 8), 0, st>>>(
+        reinterpret_cast<const float *>(ws + L.raw), reinterpret_cast<float *>(ws + L.dimg), g.H,
+        g.W, gauss3(1.0f), g.l2focus, 0, nullptr, iwes_out,
+        reinterpret_cast<double *>(ws + L.focus_partials), L.n_img_blocks);
     return check_launch();
 }
 

@@ -65,7 +65,7 @@ class _CmaxLossFunction(torch.autograd.Function):
                                   int(num_pos_events), cabi.ptr(iwes), cabi.ptr(losses), cabi.ptr(lut),
                                   cabi.ptr(ws), need, cabi.stream_ptr(dev))
             cabi.check(rc, "cmax_forward")
-        ctx.cfg = cfg
+        ctx.cfg = cfg          # the same config (incl. the backward_follows hint) must reach cmax_backward
         ctx.dims = (B, M, n, int(num_pos_events), need)
         ctx.packed = packed
         if packed:
@@ -158,6 +158,7 @@ class FocusLoss(base.TrajectoryLossBase):
             focus_loss_norm, dist_norm, scale_iwe_by_dt, mask_image_border,
             polarity_aware_batching, interpolation_scheme if num_knn > 1 else 'mean', smooth_type,
             self.deterministic, focus_loss_type)
+        self._cfg_train = cabi.with_backward_hint(self._cfg)
         cabi.load()      # fail at construction time when the CUDA library is missing
 
     def get_reconstruction_times(self, device):
@@ -183,14 +184,16 @@ class FocusLoss(base.TrajectoryLossBase):
         events = batch['events']
         if not (trajectories.is_cuda and events.is_cuda):
             raise RuntimeError("FocusLoss (B200) needs CUDA tensors; there is no CPU fallback")
+        # training (a backward will follow): the forward also emits dL/dIWE from its image pass
+        cfg = self._cfg_train if (trajectories.requires_grad and torch.is_grad_enabled()) else self._cfg
         if hasattr(events, 'seg_start'):
             # io.PackedEvents: the loader-side tile-binned layout; the polarity split is part of it
-            out = _CmaxLossFunction.apply(trajectories, times, events.records, self._cfg, 0,
+            out = _CmaxLossFunction.apply(trajectories, times, events.records, cfg, 0,
                                           bool(return_flow_lut), events.seg_start)
         else:
             num_pos_events = batch['num_pos_events'] if 'num_pos_events' in batch else -1
             assert not self.polarity_aware_batching or num_pos_events > -1
-            out = _CmaxLossFunction.apply(trajectories, times, events, self._cfg,
+            out = _CmaxLossFunction.apply(trajectories, times, events, cfg,
                                           int(num_pos_events), bool(return_flow_lut))
         loss, losses, iwes = out[0], out[1], out[2]
 

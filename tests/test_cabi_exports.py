@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_config_struct_layout_matches_header():
     from motionpriorcmax_b200 import cabi
-    assert ctypes.sizeof(cabi.CmaxConfig) == 4 * 18          # 14 int32 + float + int32 + 3 reserved
+    assert ctypes.sizeof(cabi.CmaxConfig) == 4 * 18          # 13 int32 + float + 3 int32 + 1 reserved
     assert cabi.CmaxConfig.smooth_weight.offset == 4 * 13
     assert cabi.CmaxConfig.deterministic.offset == 4 * 14
 

@@ -636,3 +636,32 @@ def test_non_power_of_two_superpixels_and_near_multiple_coordinates(s, shape):
     assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
     assert rel_err(r["iwes"], f["iwes"]) < TOL and rel_err(r["lut"], f["flow_lut"]) < TOL
     assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
+
+
+def test_backward_follows_hint_changes_nothing():
+    """CmaxConfig.backward_follows fuses the image-stage adjoint into the forward (training); a
+    forward-only call (no grad) uses the plain kernels.  Same numbers either way."""
+    from motionpriorcmax_b200 import synthetic
+    from motionpriorcmax_b200.losses import LossFactory
+    dev = _cuda()
+    for norm in ("l1", "l2"):
+        cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(96, 128), num_knn=16, focus_loss_norm=norm)
+        traj, times, ev, npos, _ = _synthetic_case(cfg, 2, [30000, 9000], 2, seed=17)
+        a = _run_loss(cfg, traj, times, ev, npos, deterministic=True)           # training path (hint on)
+        L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=True))
+        assert L._cfg.backward_follows == 0 and L._cfg_train.backward_follows == 1
+        with torch.no_grad():                                                   # inference path (hint off)
+            loss, log, misc = L.calc(torch.as_tensor(traj, device=dev), torch.as_tensor(times, device=dev),
+                                     {"events": torch.as_tensor(ev, device=dev), "num_pos_events": npos})
+        # the per-CTA partial sums are accumulated in another thread order: last-bit differences only
+        assert abs(loss.item() - a["loss"]) <= 1e-6 * abs(a["loss"])
+        assert abs(log["focus_loss"].item() - a["focus"]) <= 1e-6 * abs(a["focus"])
+        assert np.array_equal(misc["iwes"].cpu().numpy(), a["iwes"])
+        # gradient with the hint off (requires_grad, but the plain config forced)
+        L._cfg_train = L._cfg
+        t = torch.as_tensor(traj, device=dev).clone().requires_grad_()
+        loss2, _, _ = L.calc(t, torch.as_tensor(times, device=dev),
+                             {"events": torch.as_tensor(ev, device=dev), "num_pos_events": npos})
+        loss2.backward()
+        assert abs(loss2.item() - a["loss"]) <= 1e-6 * abs(a["loss"])
+        assert rel_err(t.grad.cpu().numpy(), a["dtraj"]) < 1e-6
