@@ -358,7 +358,7 @@ def run_ours(args):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
     # ---- end-to-end arm on the packed host layout (built by the loader workers, outside the step) --
-    if packed is not None and not args.no_e2e:
+    if packed is not None and not args.no_e2e and world == 1:      # host-side packing: rank-0-only leg
         pk_h = cio.pack_events_host(ev_h, npos, L).pin_memory()
         pup = cio.PackedUploader(dev, n_buffers=2)
         counts_h = pk_h.seg_start[:, -1].tolist()
