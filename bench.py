@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -507,9 +507,13 @@ def run_ours(args):
                 "value": n_ev / dt, "unit": "events/s", "cores": cores, "kind": "port",
                 "sample": f"1 window ({n_ev} events) fwd+bwd in {dt:.2f} s: numpy event stage "
                           f"(1 thread) + C/OpenMP exhaustive KNN ({cores} threads)"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as exc:            # never lose the printed line to a teardown problem
+            print(f"process-group teardown: {exc}", file=sys.stderr)
 
 
 def main():
