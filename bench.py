@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -507,7 +507,7 @@ def run_ours(args):
                 "value": n_ev / dt, "unit": "events/s", "cores": cores, "kind": "port",
                 "sample": f"1 window ({n_ev} events) fwd+bwd in {dt:.2f} s: numpy event stage "
                           f"(1 thread) + C/OpenMP exhaustive KNN ({cores} threads)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         try:
             dist.barrier()
@@ -516,7 +516,25 @@ def run_ours(args):
             print(f"process-group teardown: {exc}", file=sys.stderr)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    global _REAL_STDOUT
+    # Libraries print banners to stdout (NCCL: "NCCL version ..."): keep fd 1 for the JSON line
+    # only, send everything else to stderr.
+    try:
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        sys.stdout.flush()
+        os.dup2(2, 1)
+    except OSError:
+        _REAL_STDOUT = None
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
