@@ -245,3 +245,46 @@ def test_packed_full_size_properties():
     c = _run(cfg2, traj, times, ev, npos, "packed_dev", False)
     assert abs(a2["loss"] - c["loss"]) <= TOL * abs(a2["loss"])
     assert rel_err(c["iwes"], a2["iwes"]) < TOL and rel_err(c["dtraj"], a2["dtraj"]) < TOL
+
+
+@pytest.mark.gpu
+def test_packed_slices_empty_and_padding():
+    """Segments larger than 8 k events are cut into slices (several CTAs per tile); windows that are
+    empty or all padding, and M = 0, behave like the unpacked call."""
+    from motionpriorcmax_b200 import synthetic
+    from test_gpu_parity import _synthetic_case
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(96, 128), num_knn=16)
+    # 12 tiles x 2 groups and 400 k events per window -> ~17 k events per segment -> 3 slices
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, [400_000, 150_000], 2, seed=41, dist="edges")
+    a = _run(cfg, traj, times, ev, npos, "plain", True)
+    b = _run(cfg, traj, times, ev, npos, "packed_dev", True)
+    assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
+    # second window entirely padding
+    ev2 = ev.copy()
+    ev2[1] = 0
+    a = _run(cfg, traj, times, ev2, npos, "plain", True)
+    for mode in ("packed_dev", "packed_host"):
+        b = _run(cfg, traj, times, ev2, npos, mode, True)
+        assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
+        assert b["packed"].seg_start[:, -1].tolist() == [int(ev2[0, :, 5].sum()), 0]
+    # M = 0: no event kernel runs; 1 / mean(0) = inf like the reference
+    c = _run(cfg, traj, times, ev[:, :0], 0, "packed_dev")
+    assert np.isinf(c["loss"]) and np.abs(c["iwes"]).max() == 0.0
+
+
+@pytest.mark.gpu
+def test_packed_votes_leaving_the_image():
+    """Flows that push events across the image border (out-of-bounds corners, border mask on and
+    off): deterministic packed == deterministic unpacked, bit for bit."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    from test_gpu_parity import _synthetic_case
+    for mask in (True, False):
+        cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(64, 96), num_knn=8, num_bins=5,
+                   mask_image_border=mask)
+        traj, times, ev, npos, _ = _synthetic_case(cfg, 2, [40_000, 25_000], 1, seed=43)
+        pos = fo.tile_positions((64, 96), 4).astype(np.float32)[None, None]
+        traj = (pos + (traj - pos) * 4.0 + np.array([9.0, -7.0], np.float32)).astype(np.float32)
+        a = _run(cfg, traj, times, ev, npos, "plain", True)
+        b = _run(cfg, traj, times, ev, npos, "packed_host", True)
+        assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
