@@ -814,6 +814,73 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
     }
 }
 
+// LUT for several reference times (R > 1, mean or iwd): the window scan, not the arithmetic, is the
+// cost, so one pass serves up to four reference times (R = 5: 2 passes instead of 5).
+__global__ void __launch_bounds__(kKnnBlock)
+lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *__restrict__ cell_start,
+                            const float4 *__restrict__ sorted_all, const float *__restrict__ tau,
+                            const int *__restrict__ jcut, float *__restrict__ lut,
+                            float *__restrict__ lut_copy, float *__restrict__ wsum)
+{
+    const int tid = threadIdx.x;
+    const int64_t total = g.S * (int64_t)g.q;
+    for (int64_t sq = (int64_t)blockIdx.x * kKnnBlock + tid; sq < total; sq += (int64_t)gridDim.x * kKnnBlock) {
+        const int64_t slab = sq / g.q;
+        const Query q = make_query((int)(sq - slab * g.q), g);
+        const int *cstart = cell_start + slab * (g.NC + 1);
+        const float4 *sorted = sorted_all + slab * g.n;
+        const float t_d = tau[sq];
+        const int t_j = jcut[sq];
+        const int r = radius_for(t_d, q.cqy, q.cqx, g, q.qy, q.qx);
+        const int64_t b = slab / g.nb;
+        const float Kf = (float)g.K;
+        float S = 1.0f;
+        if (g.iwd) {
+            S = 0.0f;
+            scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                if (d < t_d || (d == t_d && __float_as_int(rec.z) <= t_j))
+                    S = __fadd_rn(S, __fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)));
+            });
+            wsum[sq] = S;
+        }
+        for (int r0 = 0; r0 < g.R; r0 += 4) {
+            const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb) + r0) * g.n;
+            const int nr = min(4, g.R - r0);
+            float ay[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+            scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
+                const int j = __float_as_int(rec.z);
+                if (d < t_d || (d == t_d && j <= t_j)) {
+                    float wgt = 1.0f;
+                    if (g.iwd) wgt = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)), S);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nr) {
+                            const float2 pr = __ldg(tref + (int64_t)c * g.n + j);
+                            float fy = __fsub_rn(pr.x, rec.x), fx = __fsub_rn(pr.y, rec.y);   // focus.py:141
+                            if (g.iwd) {
+                                fy = __fmul_rn(wgt, fy);
+                                fx = __fmul_rn(wgt, fx);
+                            }
+                            ay[c] = __fadd_rn(ay[c], fy);
+                            ax[c] = __fadd_rn(ax[c], fx);
+                        }
+                    }
+                }
+            });
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nr) {
+                    float vy = ay[c], vx = ax[c];
+                    if (!g.iwd) { vy = __fdiv_rn(vy, Kf); vx = __fdiv_rn(vx, Kf); }     // torch.mean
+                    const float2 v = make_float2(vy, vx);
+                    reinterpret_cast<float2 *>(lut)[sq * g.R + r0 + c] = v;
+                    if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq * g.R + r0 + c] = v;
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 5. backward: gather d loss / d LUT into the trajectories
 // ---------------------------------------------------------------------------------------------
@@ -823,7 +890,7 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
 // stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
 // fixed order -> deterministic, and 15x more threads in flight for the latency-bound gather.
 template <bool L1D, bool IWD, bool F2N, int RT>   // RT = compile-time R (1) or 0 = runtime R
-__global__ void __launch_bounds__(64, 24)
+__global__ void __launch_bounds__(64, RT == 1 ? 24 : 12)
 lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restrict__ tau,
                     const int *__restrict__ jcut, const float *__restrict__ wsum,
                     const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
@@ -1088,7 +1155,13 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
     float *f2n = reinterpret_cast<float *>(ws + L.f2n);
     float *wsum = reinterpret_cast<float *>(ws + L.wsum);
-    const int what = (fused ? 0 : 1) | (want_next ? 2 : 0);
+    int what = (fused ? 0 : 1) | (want_next ? 2 : 0);
+    if ((what & 1) && g.R > 1) {            // several reference times: chunked single-scan kernel
+        lut_accumulate_multi_kernel<<<acc_grid, kKnnBlock, 0, st>>>(traj, g, cell_start, sorted, tau, jcut, lut,
+                                                                    flow_lut_out, wsum);
+        count_launch();
+        what &= ~1;
+    }
     if (what) {
         lut_accumulate_kernel<<<acc_grid, kKnnBlock, 0, st>>>(
             traj, g, cell_start, sorted, tau, jcut, what, lut, flow_lut_out, f2n, wsum, nullptr, nullptr);
@@ -1102,10 +1175,13 @@ static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *t
                        const int *jcut, const float *wsum, const unsigned *tmax,
                        const unsigned *tile_max, const float *dlut, const float *df2n, float2 *part)
 {
-    if (g.R == 1)
-        lut_backward_kernel<L1D, IWD, F2N, 1><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
-    else
-        lut_backward_kernel<L1D, IWD, F2N, 0><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part);
+#define BWD_LAUNCH(RT_) lut_backward_kernel<L1D, IWD, F2N, RT_><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part)
+    if (g.R == 1) BWD_LAUNCH(1);
+    else if (!F2N && g.R == 3) BWD_LAUNCH(F2N ? 0 : 3);        // compile-time R keeps the per-reference
+    else if (!F2N && g.R == 5) BWD_LAUNCH(F2N ? 0 : 5);        // accumulators in registers (on_flow_to_next
+    else if (!F2N && g.R == 10) BWD_LAUNCH(F2N ? 0 : 10);      // implies R == 1, focus.py:51)
+    else BWD_LAUNCH(0);
+#undef BWD_LAUNCH
 }
 
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
