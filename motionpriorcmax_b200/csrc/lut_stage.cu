@@ -815,7 +815,8 @@ lut_accumulate_kernel(const float *__restrict__ traj, Geom g, const int *__restr
 }
 
 // LUT for several reference times (R > 1, mean or iwd): the window scan, not the arithmetic, is the
-// cost, so one pass serves up to four reference times (R = 5: 2 passes instead of 5).
+// cost, so one pass serves a chunk of CH reference times.
+template <int CH>
 __global__ void __launch_bounds__(kKnnBlock)
 lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *__restrict__ cell_start,
                             const float4 *__restrict__ sorted_all, const float *__restrict__ tau,
@@ -843,17 +844,19 @@ lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *_
             });
             wsum[sq] = S;
         }
-        for (int r0 = 0; r0 < g.R; r0 += 4) {
+        for (int r0 = 0; r0 < g.R; r0 += CH) {
             const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb) + r0) * g.n;
-            const int nr = min(4, g.R - r0);
-            float ay[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nr = min(CH, g.R - r0);
+            float ay[CH], ax[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) ay[c] = ax[c] = 0.0f;
             scan_window(cstart, sorted, q.cqy, q.cqx, r, g, q.qy, q.qx, [&](float d, const float4 &rec) {
                 const int j = __float_as_int(rec.z);
                 if (d < t_d || (d == t_d && j <= t_j)) {
                     float wgt = 1.0f;
                     if (g.iwd) wgt = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)), S);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < CH; ++c) {
                         if (c < nr) {
                             const float2 pr = __ldg(tref + (int64_t)c * g.n + j);
                             float fy = __fsub_rn(pr.x, rec.x), fx = __fsub_rn(pr.y, rec.y);   // focus.py:141
@@ -868,7 +871,7 @@ lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *_
                 }
             });
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CH; ++c) {
                 if (c < nr) {
                     float vy = ay[c], vx = ax[c];
                     if (!g.iwd) { vy = __fdiv_rn(vy, Kf); vx = __fdiv_rn(vx, Kf); }     // torch.mean
@@ -1157,8 +1160,17 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     float *wsum = reinterpret_cast<float *>(ws + L.wsum);
     int what = (fused ? 0 : 1) | (want_next ? 2 : 0);
     if ((what & 1) && g.R > 1) {            // several reference times: chunked single-scan kernel
-        lut_accumulate_multi_kernel<<<acc_grid, kKnnBlock, 0, st>>>(traj, g, cell_start, sorted, tau, jcut, lut,
-                                                                    flow_lut_out, wsum);
+        // chunk of reference times per window scan, measured at R = 5: 4 -> 3.14 ms, 6 -> 2.59 ms,
+        // 8 -> 2.98 ms for the K-NN stage (wider chunks pay in predicated accumulator updates)
+        if (g.R <= 4)
+            lut_accumulate_multi_kernel<4><<<acc_grid, kKnnBlock, 0, st>>>(traj, g, cell_start, sorted, tau, jcut,
+                                                                           lut, flow_lut_out, wsum);
+        else if (g.R <= 6 || g.R > 8)
+            lut_accumulate_multi_kernel<6><<<acc_grid, kKnnBlock, 0, st>>>(traj, g, cell_start, sorted, tau, jcut,
+                                                                           lut, flow_lut_out, wsum);
+        else
+            lut_accumulate_multi_kernel<8><<<acc_grid, kKnnBlock, 0, st>>>(traj, g, cell_start, sorted, tau, jcut,
+                                                                           lut, flow_lut_out, wsum);
         count_launch();
         what &= ~1;
     }
