@@ -285,7 +285,7 @@ __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
 //                (bracket wrong, list full) sends the cell to the work list - never a wrong answer.
 template <bool L1D, bool FUSED, bool GUESS>
 __global__ void __launch_bounds__(kKnnBlock, 8)
-knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
+knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_start,
                 const float4 *__restrict__ sorted_all, const float2 *__restrict__ sflow_all,
                 float *__restrict__ lut, float *__restrict__ lut_copy, float *__restrict__ tau,
                 int *__restrict__ jcut, unsigned *__restrict__ tau_max,
@@ -307,7 +307,12 @@ knn_fast_kernel(Geom g, int bin, const int *__restrict__ cell_start,
     // this grid drains; it waits (griddepcontrol.wait) before it reads this grid's tau.
     asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x;
-    const int slab = bin < 0 ? blockIdx.y : blockIdx.y * g.nb + bin;     // bin < 0: all slabs
+    // bin < 0: all slabs in one grid.  Otherwise `bin` is the step inside a chain of consecutive
+    // time bins; blockIdx.z selects the chain (independent chains share a launch so that small
+    // batches still fill the machine: EVIMO2 has 576 CTAs per bin on 1184 slots)
+    if (bin >= 0) bin += blockIdx.z * chain_len;
+    if (bin >= g.nb) return;
+    const int slab = bin < 0 ? blockIdx.y : blockIdx.y * g.nb + bin;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
@@ -1054,11 +1059,11 @@ struct FastArgs {
 };
 
 template <bool L1D, bool FUSED>
-static void launch_fast(const Geom &g, int bin, dim3 grid, cudaStream_t st, const FastArgs &a)
+static void launch_fast(const Geom &g, int bin, int chain_len, dim3 grid, cudaStream_t st, const FastArgs &a)
 {
     if (bin <= 0)
         knn_fast_kernel<L1D, FUSED, false><<<grid, kKnnBlock, 0, st>>>(
-            g, bin, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
+            g, bin, chain_len, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
             a.tile_max, a.worklist, a.work_count);
     else {
         cudaLaunchConfig_t cfg = {};
@@ -1071,8 +1076,8 @@ static void launch_fast(const Geom &g, int bin, dim3 grid, cudaStream_t st, cons
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, knn_fast_kernel<L1D, FUSED, true>, g, bin, a.cell_start, a.sorted, a.sflow,
-                           a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max, a.tile_max, a.worklist,
+        cudaLaunchKernelEx(&cfg, knn_fast_kernel<L1D, FUSED, true>, g, bin, chain_len, a.cell_start, a.sorted,
+                           a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max, a.tile_max, a.worklist,
                            a.work_count);
     }
 }
@@ -1125,21 +1130,31 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
         const FastArgs a{cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count};
         // Few samples: per-bin launches (previous-bin bracket) would serialise 15 tiny grids, so
         // run the self-contained two-pass kernel on every slab at once instead.
-        const bool per_bin = g.B >= 6;
-        dim3 grid(tiles, (unsigned)(per_bin ? g.B : g.S));
-        for (int bin = per_bin ? 0 : -1; bin < (per_bin ? g.nb : 0); ++bin) {
+        // (the inspection entry always chains, so the bracket path is testable at any batch size)
+        const bool per_bin = test_entry ? g.nb > 1 : g.B >= 6;
+        // independent chains of consecutive bins per launch until a launch fills the resident slots
+        int chains = 1;
+        if (per_bin) {
+            const int64_t ctas = (int64_t)tiles * g.B;
+            chains = (int)(148 * 8 / (ctas > 0 ? ctas : 1));
+            chains = chains < 1 ? 1 : (chains > 4 ? 4 : chains);
+            if (chains > g.nb) chains = g.nb;
+        }
+        const int chain_len = per_bin ? (g.nb + chains - 1) / chains : 0;
+        dim3 grid(tiles, (unsigned)(per_bin ? g.B : g.S), (unsigned)chains);
+        for (int bin = per_bin ? 0 : -1; bin < (per_bin ? chain_len : 0); ++bin) {
             if (g.l1dist) {
-                if (fused) launch_fast<true, true>(g, bin, grid, st, a);
-                else launch_fast<true, false>(g, bin, grid, st, a);
+                if (fused) launch_fast<true, true>(g, bin, chain_len, grid, st, a);
+                else launch_fast<true, false>(g, bin, chain_len, grid, st, a);
             } else {
-                if (fused) launch_fast<false, true>(g, bin, grid, st, a);
-                else launch_fast<false, false>(g, bin, grid, st, a);
+                if (fused) launch_fast<false, true>(g, bin, chain_len, grid, st, a);
+                else launch_fast<false, false>(g, bin, chain_len, grid, st, a);
             }
         }
         knn_heap_kernel<<<148 * 16, kKnnBlock, smem_heap / 4, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
                                                                   tau_max, tile_max, worklist, work_count,
                                                                   fused ? 1 : 0, lut, lc, 8);
-        count_launch((per_bin ? g.nb : 1) + 1);
+        count_launch((per_bin ? chain_len : 1) + 1);
     } else {
         cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
         knn_heap_kernel<<<148 * 8, kKnnBlock, smem_heap, st>>>(traj, g, -1, cell_start, sorted, tau, jcut,

@@ -665,3 +665,22 @@ def test_backward_follows_hint_changes_nothing():
         loss2.backward()
         assert abs(loss2.item() - a["loss"]) <= 1e-6 * abs(a["loss"])
         assert rel_err(t.grad.cpu().numpy(), a["dtraj"]) < 1e-6
+
+
+@pytest.mark.parametrize("B", [6, 9])
+def test_per_bin_chain_batches_match_oracle(B):
+    """Batches of >= 6 windows take the per-bin launch chain of the K-NN stage (previous-bin
+    bracket, several independent chains per launch when the batch is small) - the path the DSEC /
+    EVIMO2 training shapes use.  LUT, loss and gradient against the float64 oracle."""
+    from motionpriorcmax_b200 import synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(64, 96), num_knn=12, num_bins=7)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, B, [6000 + 500 * i for i in range(B)], 2, seed=50 + B)
+    r = _run_loss(cfg, traj, times, ev, npos)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(traj, times, ev, npos)
+    g = o.backward()
+    assert abs(r["loss"] - f["loss"]) <= TOL * abs(f["loss"])
+    assert rel_err(r["lut"], f["flow_lut"]) < TOL
+    assert rel_err(r["iwes"], f["iwes"]) < TOL
+    _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos, gpu_iwes=r["iwes"])
