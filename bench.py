@@ -359,7 +359,7 @@ def run_ours(args):
         ms_e2e = f0.elapsed_time(f1)
     # ---- end-to-end arm on the packed host layout (built by the loader workers, outside the step) --
     if packed is not None and not args.no_e2e and world == 1:      # host-side packing: rank-0-only leg
-        pk_h = cio.pack_events_host(ev_h, npos, L).pin_memory()
+        pk_h = cio.pack_events_native(ev_h, npos, L).pin_memory()      # C++ / OpenMP host packer (loader side)
         pup = cio.PackedUploader(dev, n_buffers=2)
         counts_h = pk_h.seg_start[:, -1].tolist()
         ppending = {}
@@ -498,8 +498,8 @@ def run_ours(args):
                     "value_rank0": n_valid / (packed["ms_e2e"] / args.steps * 1e-3), "unit": "events/s",
                     "ms_per_step": packed["ms_e2e"] / args.steps,
                     "h2d_bytes_per_step": packed["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
-                    "note": "pinned host PackedEvents (io.pack_events_host in the loader workers) copied in "
-                            "every step, loss read back"}
+                    "note": "pinned host PackedEvents (io.pack_events_native / cmax_pack_events_host in the loader "
+                            "workers, outside the step) copied in every step, loss read back"}
         if world == 1 and not args.no_cpu:
             dt, n_ev = cpu_reference_step(cfg, w, cg_h, ev_h, npos)
             cores = os.cpu_count() or 1

@@ -124,6 +124,15 @@ int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int6
                      int64_t num_pos_events, float *records_out, int32_t *seg_start_out,
                      int32_t *scratch, int64_t *skipped_out, void *stream);
 
+/* HOST builder of the same layout for DataLoader workers (C++ / OpenMP over the windows, no CUDA
+ * call): all pointers are HOST pointers.  A stable counting sort - the row order inside every
+ * segment is kept, so the result equals io.pack_events_host byte for byte.
+ *   records_host [B, records_stride, 4] (may be NULL: a first call that only fills seg_start tells
+ *   the caller how many records each window needs, seg_start[b, G*NT]); skipped_host int64[2]. */
+int cmax_pack_events_host(const CmaxConfig *cfg, const float *events_host, int64_t B, int64_t M,
+                          int64_t num_pos_events, float *records_host, int64_t records_stride,
+                          int32_t *seg_start_host, int64_t *skipped_host);
+
 /* cmax_forward / cmax_backward on the packed layout: same outputs, same workspace
  * (cmax_workspace_bytes(cfg, B, M, n) with the M of `records`).  The event stage accumulates
  * the IWE votes of a (tile, group) segment in a shared-memory window and flushes once; votes

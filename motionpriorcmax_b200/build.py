@@ -35,7 +35,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.join(CSRC, "host_pack.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -53,6 +53,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
+    # host-only translation unit (loader-side packer): g++ with OpenMP
+    hobj = os.path.join(OUT_DIR, "host_pack.o")
+    hcmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-fopenmp", "-c", os.path.join(CSRC, "host_pack.cpp"), "-o", hobj]
+    if verbose:
+        print(" ".join(hcmd))
+    subprocess.run(hcmd, check=True)
+    objs.append(hobj)
     for s, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
@@ -60,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
     cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-cudart", "shared"]
+           "-Xcompiler", "-fPIC", "-cudart", "shared", "-lgomp"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -26,7 +26,7 @@ EXPORTS = (
     "cmax_last_worklist_count", "cmax_voxel_grid", "cmax_dense_flow",
     "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
     "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
-    "cmax_backward_accumulate", "cmax_backward_finish",
+    "cmax_backward_accumulate", "cmax_backward_finish", "cmax_pack_events_host",
 )
 
 
@@ -70,6 +70,8 @@ def load():
     lib.cmax_pack_layout.argtypes = [POINTER(CmaxConfig), POINTER(c_int32 * 4)]
     lib.cmax_pack_events.restype = c_int32
     lib.cmax_pack_events.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, P, P, P, P]
+    lib.cmax_pack_events_host.restype = c_int32
+    lib.cmax_pack_events_host.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, c_int64, P, P]
     lib.cmax_forward_packed.restype = c_int32
     lib.cmax_forward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
                                         P, P, P, P, c_size_t, P]

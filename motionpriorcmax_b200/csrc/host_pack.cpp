@@ -1,0 +1,130 @@
+// host_pack.cpp - HOST-side builder of the packed, tile-binned event layout (include/cmax_b200.h),
+// for DataLoader workers / the collate function.  Replaces the producer of the `events` tensor
+// (upstream src/loader/dsec/loader.py:141-182,360-415) for the loss path; plain C++ + OpenMP, no
+// CUDA call.  Produces exactly what motionpriorcmax_b200.io.pack_events_host (torch CPU ops, stable
+// sort) produces: a counting sort by (polarity group, source tile) that keeps the row order inside
+// every segment.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/cmax_b200.h"
+
+namespace {
+
+// torch's `//` on float32 (c10::div_floor_floating), the arithmetic of focus.py:186-187
+inline float floordiv_f32(float a, float b)
+{
+    const float mod = fmodf(a, b);
+    float div = (a - mod) / b;
+    if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div -= 1.0f;
+    float fd;
+    if (div != 0.0f) {
+        fd = floorf(div);
+        if (div - fd > 0.5f) fd += 1.0f;
+    } else {
+        fd = copysignf(0.0f, a / b);
+    }
+    return fd;
+}
+
+struct HostLayout {
+    int s, nb, Hq, Wq, ct, nty, ntx, nt, G;
+};
+
+bool host_layout(const CmaxConfig *c, HostLayout *L)
+{
+    int32_t out[4];
+    if (cmax_pack_layout(c, out) != CMAX_OK) return false;
+    L->s = c->lut_superpixel_size;
+    L->nb = c->num_bins;
+    L->Hq = (c->height + L->s - 1) / L->s;
+    L->Wq = (c->width + L->s - 1) / L->s;
+    L->ct = out[0];
+    L->nty = out[1];
+    L->ntx = out[2];
+    L->nt = L->nty * L->ntx;
+    L->G = out[3];
+    return true;
+}
+
+// segment key and meta word of one row; -1: dropped (padding), -2: dropped (cell outside the table)
+inline int row_key(const float *row, int64_t m, int64_t npos, const HostLayout &L, uint32_t *meta)
+{
+    const float valid = row[5];
+    if (valid == 0.0f) return -1;
+    const float fs = (float)L.s;
+    const float fy = floordiv_f32(row[0], fs), fx = floordiv_f32(row[1], fs);
+    const float ft = truncf(row[4]);
+    if (!(ft >= 0.0f && ft < (float)L.nb && fy >= 0.0f && fy < (float)L.Hq && fx >= 0.0f && fx < (float)L.Wq))
+        return -2;
+    const int it = (int)ft, iy = (int)fy, ix = (int)fx;
+    const int grp = (L.G == 2 && m >= npos) ? 1 : 0;
+    *meta = ((uint32_t)it << 24) | ((uint32_t)iy << 12) | (uint32_t)ix;
+    return grp * L.nt + (iy / L.ct) * L.ntx + ix / L.ct;
+}
+
+}  // namespace
+
+extern "C" int cmax_pack_events_host(const CmaxConfig *cfg, const float *events_host, int64_t B,
+                                     int64_t M, int64_t num_pos_events, float *records_host,
+                                     int64_t records_stride, int32_t *seg_start_host,
+                                     int64_t *skipped_host)
+{
+    HostLayout L;
+    if (!cfg) return CMAX_ERR_BAD_CONFIG;
+    if (!host_layout(cfg, &L)) return CMAX_ERR_UNSUPPORTED;
+    if (B < 0 || M < 0 || (!events_host && B * M > 0) || !seg_start_host) return CMAX_ERR_BAD_SHAPE;
+    if (L.G == 2 && (num_pos_events < 0 || num_pos_events > M)) return CMAX_ERR_BAD_SHAPE;
+    if (M > (int64_t)INT32_MAX) return CMAX_ERR_UNSUPPORTED;
+    const int nkeys = L.G * L.nt;
+    int64_t dropped = 0, odd = 0;
+    int rc = CMAX_OK;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : dropped, odd)
+    for (int64_t b = 0; b < B; ++b) {
+        const float *ev = events_host + b * M * 6;
+        int32_t *seg = seg_start_host + b * (int64_t)(nkeys + 1);
+        std::vector<int32_t> key((size_t)M);
+        std::vector<uint32_t> meta((size_t)M);
+        std::vector<int32_t> cursor((size_t)nkeys + 1, 0);
+        for (int64_t m = 0; m < M; ++m) {
+            uint32_t mw = 0;
+            const int k = row_key(ev + m * 6, m, num_pos_events, L, &mw);
+            key[(size_t)m] = k;
+            meta[(size_t)m] = mw;
+            if (k >= 0) {
+                ++cursor[(size_t)k + 1];
+                if (ev[m * 6 + 5] != 1.0f) ++odd;
+            } else if (k == -2) {
+                ++dropped;
+                if (ev[m * 6 + 5] != 1.0f) ++odd;
+            }
+        }
+        for (int k = 0; k < nkeys; ++k) cursor[(size_t)k + 1] += cursor[(size_t)k];
+        memcpy(seg, cursor.data(), sizeof(int32_t) * (size_t)(nkeys + 1));
+        if (records_host) {
+            if (cursor[(size_t)nkeys] > records_stride) {
+#pragma omp critical
+                rc = CMAX_ERR_BAD_SHAPE;              // records_stride too small for this window
+                continue;
+            }
+            float *rec = records_host + b * records_stride * 4;
+            for (int64_t m = 0; m < M; ++m) {
+                const int k = key[(size_t)m];
+                if (k < 0) continue;
+                float *dst = rec + (int64_t)cursor[(size_t)k]++ * 4;
+                dst[0] = ev[m * 6 + 0];
+                dst[1] = ev[m * 6 + 1];
+                dst[2] = ev[m * 6 + 2];
+                memcpy(dst + 3, &meta[(size_t)m], 4);
+            }
+        }
+    }
+    if (skipped_host) {
+        skipped_host[0] = dropped;
+        skipped_host[1] = odd;
+    }
+    return rc;
+}

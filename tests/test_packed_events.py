@@ -92,6 +92,46 @@ def test_host_packer_layout_contract(s, pab):
     assert _segments(pk2, layout) == want
 
 
+@pytest.mark.parametrize("s,pab", [(4, True), (3, False), (16, True)])
+def test_native_host_packer_equals_torch_host_packer(s, pab):
+    """cmax_pack_events_host (C++ / OpenMP, host pointers only - no GPU involved) against
+    io.pack_events_host: same segments, same records in the same order, same drop counters."""
+    from motionpriorcmax_b200 import io, synthetic
+    H, W, nb = 120, 150, 9
+    d = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(H, W), num_bins=nb, lut_superpixel_size=s,
+             num_knn=2, polarity_aware_batching=pab)
+    cfg = _cfg(d)
+    ev, npos = synthetic.make_event_batch(4, [9000, 4000, 0, 12000], H, W, nb, pab, seed=6)
+    ev = ev.clone()
+    rng = np.random.default_rng(1)
+    k = 400
+    # coordinates a few ulp around cell edges, rows outside the table, NaN / inf, odd `valid`
+    edge = (rng.integers(0, H // s + 2, k) * s).astype(np.float32)
+    ev[0, :k, 0] = torch.as_tensor(edge + rng.choice(np.array([-2e-6, -1e-6, 0, 1e-6, 1e-5], np.float32), k))
+    ev[0, k:k + 50, 1] = -0.25
+    ev[1, :30, 4] = float(nb)
+    ev[1, 40, 0] = float("nan")
+    ev[1, 41, 1] = float("inf")
+    ev[1, 42, 4] = float("nan")
+    ev[3, 7, 5] = 0.5
+    a = io.pack_events_host(ev, npos, cfg)
+    b = io.pack_events_native(ev, npos, cfg)
+    assert torch.equal(a.seg_start, b.seg_start)
+    assert a.skipped.tolist() == b.skipped.tolist() and int(a.skipped[0]) >= 80
+    for i, c in enumerate(a.seg_start[:, -1].tolist()):
+        assert torch.equal(a.records[i, :c].view(torch.int32), b.records[i, :c].view(torch.int32)), i
+    # capacity too small for a window -> error code, not an overflow
+    from motionpriorcmax_b200 import cabi
+    import ctypes
+    lib = cabi.load()
+    rec = torch.zeros((4, 10, 4))
+    seg = torch.zeros_like(a.seg_start)
+    e = ev.contiguous()
+    rc = lib.cmax_pack_events_host(cfg, ctypes.c_void_p(e.data_ptr()), 4, e.shape[1], npos if pab else 0,
+                                   ctypes.c_void_p(rec.data_ptr()), 10, ctypes.c_void_p(seg.data_ptr()), None)
+    assert rc == -2
+
+
 def test_pack_layout_query_and_limits():
     from motionpriorcmax_b200 import cabi, synthetic
     lib = cabi.load()
