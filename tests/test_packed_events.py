@@ -132,6 +132,26 @@ def test_native_host_packer_equals_torch_host_packer(s, pab):
     assert rc == -2
 
 
+def test_packed_collate_example_pickles_and_packs():
+    """examples/packed_collate.py: the drop-in collate survives pickling (worker processes) and
+    yields the layout of the host packer."""
+    import os
+    import pickle
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    from packed_collate import PackedCollate
+    from motionpriorcmax_b200 import io, synthetic
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(64, 96), num_bins=5, num_knn=4)
+    ev, npos = synthetic.make_event_batch(3, [3000, 1000, 2000], 64, 96, 5, True, seed=12)
+    collate = pickle.loads(pickle.dumps(PackedCollate(cfg)))
+    batch = collate({"events": ev, "num_pos_events": npos, "other": 1})
+    ref = io.pack_events_host(ev, npos, collate._config())
+    assert batch["other"] == 1 and torch.equal(batch["events"].seg_start, ref.seg_start)
+    for b, c in enumerate(ref.seg_start[:, -1].tolist()):
+        assert torch.equal(batch["events"].records[b, :c].view(torch.int32), ref.records[b, :c].view(torch.int32))
+    pickle.dumps(collate)                       # still picklable after the config was built
+
+
 def test_pack_layout_query_and_limits():
     from motionpriorcmax_b200 import cabi, synthetic
     lib = cabi.load()
