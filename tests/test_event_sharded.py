@@ -138,3 +138,25 @@ def test_virtual_ranks_match_unsharded(variant, world):
         assert abs(r["loss"] - ref2["loss"]) <= TOL * abs(ref2["loss"])
         assert rel_err(r["iwes"].reshape(ref2["iwes"].shape), ref2["iwes"]) < TOL
         assert rel_err(r["dtraj"], ref2["dtraj"]) < TOL
+
+
+def test_sharding_is_additive_for_the_reference_algorithm():
+    """CPU, oracle only: the raw IWE of the reference algorithm is additive over any split of the
+    event rows (what the first all-reduce of the sharded mode relies on), and the row-sharding
+    helper produces such a split."""
+    from motionpriorcmax_b200 import synthetic
+    from motionpriorcmax_b200.losses.sharded import shard_event_rows
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(48, 64), num_knn=6, num_bins=5)
+    H, W = cfg["image_shape"]
+    times = fo.reconstruction_times(1, cfg["num_bins"], 0.6)
+    cg = synthetic.make_coeff_grid(2, 1, H, W, sigma_px=5.0, seed=8, coarse=(4, 5)).numpy()
+    traj, _ = fo.trajectories_from_coeff_grid(cg, times, 4, 1, "polynomial")
+    ev, npos = synthetic.make_event_batch(2, [3000, 1700], H, W, cfg["num_bins"], True, seed=8)
+    full = fo.FocusOracle(**cfg, dtype=np.float64).forward(traj, times, ev.numpy(), npos)
+    for world in (2, 3):
+        raw = 0.0
+        for r in range(world):
+            sh, np_r = shard_event_rows(ev, npos, r, world)
+            raw = raw + fo.FocusOracle(**cfg, dtype=np.float64).forward(traj, times, sh.numpy(), np_r)["iwe_raw"]
+        assert rel_err(raw, full["iwe_raw"]) < 1e-12

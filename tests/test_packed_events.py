@@ -348,3 +348,32 @@ def test_packed_votes_leaving_the_image():
         a = _run(cfg, traj, times, ev, npos, "plain", True)
         b = _run(cfg, traj, times, ev, npos, "packed_host", True)
         assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
+
+
+def test_packing_is_neutral_for_the_reference_algorithm():
+    """CPU, oracle only: the reference algorithm (float64 restatement) gives the same loss, IWEs
+    and gradients on unpack(pack(events)) as on the collated batch - dropping the padding rows and
+    regrouping the events by tile changes nothing but the summation order."""
+    from motionpriorcmax_b200 import io, synthetic
+    from oracle import focus_oracle as fo
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(48, 64), num_knn=6, num_bins=5)
+    H, W = cfg["image_shape"]
+    times = fo.reconstruction_times(1, cfg["num_bins"], 0.37)
+    cg = synthetic.make_coeff_grid(2, 2, H, W, sigma_px=5.0, seed=4, coarse=(4, 5)).numpy()
+    traj, _ = fo.trajectories_from_coeff_grid(cg, times, 4, 2, "polynomial")
+    ev, npos = synthetic.make_event_batch(2, [2500, 1200], H, W, cfg["num_bins"], True, seed=4)
+    c = _cfg(cfg)
+    ct = 8
+    layout = (ct, -(-(H // 4) // ct), -(-(W // 4) // ct), 2)
+    pk = io.pack_events_host(ev, npos, c, layout=layout)
+    assert int(pk.skipped[0]) == 0
+    ev2, npos2 = io.unpack_events(pk, c, layout=layout)
+    a = fo.FocusOracle(**cfg, dtype=np.float64)
+    fa = a.forward(traj, times, ev.numpy(), npos)
+    ga = a.backward()
+    b = fo.FocusOracle(**cfg, dtype=np.float64)
+    fb = b.forward(traj, times, ev2.numpy(), npos2)
+    gb = b.backward()
+    assert abs(fa["loss"] - fb["loss"]) <= 1e-12 * abs(fa["loss"])
+    assert rel_err(fb["iwes"], fa["iwes"]) < 1e-12
+    assert rel_err(gb["dtraj"], ga["dtraj"]) < 1e-10
