@@ -177,8 +177,16 @@ def pack_events(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg
     return PackedEvents(rec, seg, skipped)
 
 
+def _check_binary_valid(odd: int, strict: bool):
+    if odd and strict:
+        raise ValueError(
+            f"{odd} event rows have a `valid` value that is neither 0 nor 1: the packed layout keeps no "
+            "per-event weight (the reference multiplies the vote by `valid`, focus.py:201). Use the "
+            "[B, M, 6] layout for weighted events, or pass strict=False to treat them as valid = 1.")
+
+
 def pack_events_host(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
-                     layout=None) -> PackedEvents:
+                     layout=None, strict: bool = True) -> PackedEvents:
     """The same layout built with torch CPU ops - for DataLoader workers / the collate function.
     `layout` = (ct, tiles_y, tiles_x, G) avoids loading the CUDA library in a worker process; by
     default it is asked from the library (`cabi.pack_layout`)."""
@@ -203,6 +211,7 @@ def pack_events_host(events: torch.Tensor, num_pos_events: Optional[int], loss_o
         & (ev[..., 4] == ev[..., 4])
     dropped = int(((ev[..., 5] != 0) & ~ok).sum())
     odd = int(((ev[..., 5] != 0) & (ev[..., 5] != 1)).sum())
+    _check_binary_valid(odd, strict)
     iy = torch.where(ok, fy, torch.zeros_like(fy)).to(torch.int64)
     ix = torch.where(ok, fx, torch.zeros_like(fx)).to(torch.int64)
     it = torch.where(ok, it, torch.zeros_like(it))
@@ -223,7 +232,8 @@ def pack_events_host(events: torch.Tensor, num_pos_events: Optional[int], loss_o
     return PackedEvents(rec, seg.to(torch.int32), torch.tensor([dropped, odd], dtype=torch.int64))
 
 
-def pack_events_native(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg) -> PackedEvents:
+def pack_events_native(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
+                       strict: bool = True) -> PackedEvents:
     """`pack_events_host` through the C ABI (`cmax_pack_events_host`: C++ / OpenMP counting sort,
     one thread per window): the same records and segments (byte for byte), several times faster
     than the torch sort (8 windows of 1 M events on 8 cores: 0.18 s vs 0.62 s).  CPU tensors
@@ -244,6 +254,7 @@ def pack_events_native(events: torch.Tensor, num_pos_events: Optional[int], loss
     # pass 1: segment sizes only (records = NULL) -> the record capacity the batch needs
     cabi.check(lib.cmax_pack_events_host(cfg, p(ev), B, M, npos, None, 0, p(seg), p(skipped)),
                "cmax_pack_events_host")
+    _check_binary_valid(int(skipped[1]), strict)
     Mp = max(int(seg[:, -1].max()) if B else 0, 1)
     rec = torch.zeros((B, Mp, 4), dtype=torch.float32)
     cabi.check(lib.cmax_pack_events_host(cfg, p(ev), B, M, npos, p(rec), Mp, p(seg), p(skipped)),

@@ -114,10 +114,13 @@ def test_native_host_packer_equals_torch_host_packer(s, pab):
     ev[1, 41, 1] = float("inf")
     ev[1, 42, 4] = float("nan")
     ev[3, 7, 5] = 0.5
-    a = io.pack_events_host(ev, npos, cfg)
-    b = io.pack_events_native(ev, npos, cfg)
+    for packer in (io.pack_events_host, io.pack_events_native):      # a weighted row is refused by default
+        with pytest.raises(ValueError, match="neither 0 nor 1"):
+            packer(ev, npos, cfg)
+    a = io.pack_events_host(ev, npos, cfg, strict=False)
+    b = io.pack_events_native(ev, npos, cfg, strict=False)
     assert torch.equal(a.seg_start, b.seg_start)
-    assert a.skipped.tolist() == b.skipped.tolist() and int(a.skipped[0]) >= 80
+    assert a.skipped.tolist() == b.skipped.tolist() and int(a.skipped[0]) >= 80 and int(a.skipped[1]) == 1
     for i, c in enumerate(a.seg_start[:, -1].tolist()):
         assert torch.equal(a.records[i, :c].view(torch.int32), b.records[i, :c].view(torch.int32)), i
     # capacity too small for a window -> error code, not an overflow
