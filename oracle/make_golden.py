@@ -72,6 +72,9 @@ CASES = {
     # the reference's other focus functional (src/utils/loss.py:14-16); FocusLoss.calc hard-codes
     # 'gradient_magnitude' (focus.py:90), so the call is redirected for this case only
     "variance_functional": (cfgv(), dict(B=2, M=700, K=1, basis="polynomial", patch=4, variance=True)),
+    # six windows: the batch size from which the CUDA path chains its per-bin K-NN launches
+    "chain_b6_k12": (cfgv(image_shape=(48, 64), num_bins=7, num_knn=12),
+                     dict(B=6, M=[1500, 2200, 900, 1800, 2500, 1200], K=2, basis="polynomial", patch=4)),
 }
 
 
