@@ -283,6 +283,7 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     stage = cabi.stage_timing_read()
+    worklist = cabi.worklist_reasons(cabi.stream_ptr(dev))      # of the last step's K-NN stage
     lib.cmax_stage_timing_enable(0)
     launches = lib.cmax_launch_count() - launches0
 
@@ -474,7 +475,8 @@ def run_ours(args):
                          "event_kernels": ev_roof,
                          "note": "the dominant stage is the exact K-NN LUT build: a fixed per-window "
                                  "cost that is instruction/latency bound, not HBM bound",
-                         "stage_ms_per_launch": per_launch},
+                         "stage_ms_per_launch": per_launch,
+                         "knn_worklist_cells": worklist},
             "e2e": {"value": e2e_val, "unit": "events/s",
                     "h2d_bytes_per_step": int(up.bytes_last + cg_p.numel() * 4),
                     "h2d_note": "valid event rows only (padding rows are zero-filled on the device)",

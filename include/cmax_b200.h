@@ -253,6 +253,11 @@ int64_t cmax_launch_count(void);
 /* Inspection: how many LUT queries of the most recent cmax_forward / cmax_knn_indices call left
  * the staged fast path for the heap search (host call, synchronises `stream`; -1 if unknown). */
 int64_t cmax_last_worklist_count(void *stream);
+/* Same call, split by reason: out[0] = cells that left the staged kernel, out[1..7] = window not
+ * staged (too many points), no usable bracket, fewer than K / more than 255 points in the window,
+ * K-th key beyond the window's guaranteed bound, boundary list full, previous-bin bracket missed;
+ * out[8] = cells the warp-cooperative work-list kernel passed on to the heap search; rest reserved. */
+int cmax_last_worklist_reasons(int64_t out_host[16], void *stream);
 
 /* Reads the status words the kernels keep in the workspace (host call, synchronises `stream`):
  * out[0] = events skipped because their LUT cell index was out of range, out[1..3] reserved. */

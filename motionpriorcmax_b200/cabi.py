@@ -23,7 +23,7 @@ EXPORTS = (
     "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
     "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
-    "cmax_last_worklist_count", "cmax_voxel_grid", "cmax_dense_flow",
+    "cmax_last_worklist_count", "cmax_last_worklist_reasons", "cmax_voxel_grid", "cmax_dense_flow",
     "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
     "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
     "cmax_backward_accumulate", "cmax_backward_finish", "cmax_pack_events_host",
@@ -127,6 +127,8 @@ def load():
     lib.cmax_launch_count.restype = c_int64
     lib.cmax_last_worklist_count.restype = c_int64
     lib.cmax_last_worklist_count.argtypes = [P]
+    lib.cmax_last_worklist_reasons.restype = c_int32
+    lib.cmax_last_worklist_reasons.argtypes = [P, P]
     if lib.cmax_abi_version() != 1:
         raise RuntimeError("libcmax_b200.so ABI version mismatch")
     _lib = lib
@@ -201,6 +203,15 @@ def stage_timing_read():
     check(lib.cmax_stage_timing_read(ctypes.cast(ms, c_void_p), ctypes.cast(cnt, c_void_p)),
           "cmax_stage_timing_read")
     return {lib.cmax_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+
+
+def worklist_reasons(stream=None):
+    """Inspection: how many LUT cells of the most recent forward left the staged fast path, by reason."""
+    out = (ctypes.c_int64 * 16)()
+    check(load().cmax_last_worklist_reasons(ctypes.cast(out, c_void_p), stream), "cmax_last_worklist_reasons")
+    names = ("total", "window_not_staged", "no_bracket", "fewer_than_k_in_window", "more_than_255_in_window",
+             "kth_beyond_window_bound", "boundary_list_full", "previous_bin_bracket_missed", "heap_fallback")
+    return {k: int(out[i]) for i, k in enumerate(names)}
 
 
 def ptr(t) -> c_void_p:

@@ -148,7 +148,8 @@ static void take_knn(const Geom &g, Layout &L, Take &take)
     L.tau_max = take(sizeof(unsigned) * g.S);
     L.tile_max = take(sizeof(unsigned) * g.S * tiles);
     L.worklist = take(sizeof(int) * g.S * g.q);
-    L.work_count = take(sizeof(int) * g.nb);
+    L.worklist2 = take(sizeof(int) * g.S * g.q);
+    L.work_count = take(sizeof(int) * 16);        // [0] work-list length, [1..7] miss reasons, [8] second list
 }
 
 Layout make_knn_layout(const Geom &g)
@@ -771,6 +772,17 @@ int64_t cmax_last_worklist_count(void *stream)
     if (cudaMemcpyAsync(&v, g_last_work_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     return v;
+}
+
+int cmax_last_worklist_reasons(int64_t out_host[16], void *stream)
+{
+    if (!g_last_work_count || !out_host) return CMAX_ERR_WORKSPACE;
+    int v[16] = {};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(v, g_last_work_count, sizeof(v), cudaMemcpyDeviceToHost, st) != cudaSuccess) return CMAX_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return CMAX_ERR_CUDA;
+    for (int i = 0; i < 16; ++i) out_host[i] = v[i];
+    return CMAX_OK;
 }
 
 int cmax_read_status(const void *workspace, int64_t out_host[4], void *stream)

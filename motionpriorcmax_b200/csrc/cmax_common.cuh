@@ -37,6 +37,7 @@ struct Geom {                 // derived sizes, passed by value to kernels
     int r_fast;               // window radius of the staged fast path
     int l1dist, l2focus, scale_dt, mask_border, pab, iwd, smooth_next, det, variance;
     int fuse_image;           // training hint: the forward also produces dL/dIWE (image stage fused)
+    int dbg;                  // experiment switches (CMAX_FWD_OPT), 0 in production
     float smooth_w;
     int64_t B, M, n, S;       // S = B * nb
     int64_t npos;
@@ -53,7 +54,7 @@ struct Header {               // first 1 KiB of the workspace
 
 struct Layout {
     size_t header, focus_partials, plane_stats, smooth_partials, cell_start, sorted, sflow, tau, jcut, wsum,
-        tau_max, tile_max, worklist, work_count, bpart, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
+        tau_max, tile_max, worklist, worklist2, work_count, bpart, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
     int n_img_blocks, n_sm_blocks;
 };
 

@@ -26,6 +26,8 @@
 //                          with bit-identical distance arithmetic); the search window is bounded
 //                          per 16x8-query tile by that tile's largest tau.  No atomics, no K-index
 //                          tensor in HBM: 8 B per query (tau, jcut) is all the backward needs.
+#include <stdlib.h>
+
 #include "cmax_common.cuh"
 
 namespace cmax {
@@ -264,8 +266,9 @@ __device__ __forceinline__ Query make_query(int c, const Geom &g)
 // ---------------------------------------------------------------------------------------------
 // 2. fast path
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 1024;    // points staged per CTA
-constexpr int kListCap = 20;       // boundary candidates kept per thread
+constexpr int kStageCap = 960;     // staged records per CTA (points + 3 sentinels per window row)
+constexpr int kListCap = 24;       // boundary candidates kept per thread
+constexpr int kRowPad = 3;         // sentinel records after every staged window row
 constexpr int kWinRows = kKnnTileH + 2 * 10;
 constexpr int kWinCols = kKnnTileW + 2 * 10;
 constexpr float kGuessLo = 0.82f;  // bracket around the previous bin's K-th key
@@ -275,7 +278,48 @@ constexpr float kGuessHi = 1.22f;
 __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
 {
     const float v = __fmul_rn(__fsub_rn(d, lo), invw);
-    return d < lo ? 0 : min(__float2int_rd(v) + 1, 8);
+    return d < lo ? 0 : (v == v ? min(__float2int_rd(v) + 1, 8) : 8);     // NaN distance: never a candidate
+}
+
+// staged record: (y, x) and, when the LUT entry is fused into the selection, the flow to t_ref
+template <bool FUSED> struct StageRec { typedef float2 T; };
+template <> struct StageRec<true> { typedef float4 T; };
+__device__ __forceinline__ float2 rec_flow(const float4 &r) { return make_float2(r.z, r.w); }
+__device__ __forceinline__ float2 rec_flow(const float2 &) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ float4 make_rec(float y, float x, float2 f, float4 *) { return make_float4(y, x, f.x, f.y); }
+__device__ __forceinline__ float2 make_rec(float y, float x, float2, float2 *) { return make_float2(y, x); }
+
+// One candidate of the single-pass bracket scan, branch free (a branch per outcome splits every
+// warp: the three outcomes are about 55 % / 20 % / 25 % of the candidates):
+//   d <  lo        sure member: count it and (FUSED) add its flow
+//   lo <= d < hi   bracket candidate: append its staged index to the thread's list
+// `lp` is the shared-memory address of the next free list slot (stride = one u16 row of the CTA).
+template <bool FUSED>
+__device__ __forceinline__ void classify(float d, float lo, float hi, float2 f, int idx, int &below,
+                                         float &ay, float &ax, unsigned &lp)
+{
+    if (FUSED)
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.lt.f32 p, %4, %5;\n\t"
+            "setp.lt.and.f32 q, %4, %6, !p;\n\t"
+            "@p add.rn.f32 %0, %0, %7;\n\t"
+            "@p add.rn.f32 %1, %1, %8;\n\t"
+            "@p add.s32 %2, %2, 1;\n\t"
+            "@q st.shared.u16 [%3], %9;\n\t"
+            "@q add.u32 %3, %3, %10;\n\t}"
+            : "+f"(ay), "+f"(ax), "+r"(below), "+r"(lp)
+            : "f"(d), "f"(lo), "f"(hi), "f"(f.x), "f"(f.y), "h"((unsigned short)idx), "n"(kKnnBlock * 2)
+            : "memory");
+    else
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.lt.f32 p, %2, %3;\n\t"
+            "setp.lt.and.f32 q, %2, %4, !p;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t"
+            "@q st.shared.u16 [%1], %5;\n\t"
+            "@q add.u32 %1, %1, %6;\n\t}"
+            : "+r"(below), "+r"(lp)
+            : "f"(d), "f"(lo), "f"(hi), "h"((unsigned short)idx), "n"(kKnnBlock * 2)
+            : "memory");
 }
 
 // GUESS = false: self-contained two-pass histogram select (first bin of a sample).
@@ -292,13 +336,12 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                 unsigned *__restrict__ tile_max, int *__restrict__ worklist,
                 int *__restrict__ work_count)
 {
-    __shared__ float s_py[kStageCap], s_px[kStageCap];
+    typedef typename StageRec<FUSED>::T Rec;
+    __shared__ Rec s_pt[kStageCap];
     __shared__ int s_pj[kStageCap];
-    __shared__ float2 s_fl[FUSED ? kStageCap : 1];
     __shared__ unsigned short s_cell[kWinRows][kWinCols + 1];     // local run starts (< kStageCap)
     // boundary candidates: only the staged index is kept (u16, + the slice id in bits 10..13);
-    // distances are recomputed from the staged point on demand - 40 B instead of 160 B per thread
-    // buys two more resident CTAs per SM
+    // distances are recomputed from the staged point on demand
     __shared__ unsigned short s_li[kListCap][kKnnBlock];
     __shared__ int s_rowbase[kWinRows + 1];
     __shared__ unsigned blk_max;
@@ -317,24 +360,38 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
     const bool active = iy < g.Hq && ix < g.Wq;
-    const int r = g.r_fast;
     const int *cstart = cell_start + (int64_t)slab * (g.NC + 1);
     const float4 *sorted = sorted_all + (int64_t)slab * g.n;
 
     // ---- the tile's cell window -----------------------------------------------------------
+    // radius r_fast in the interior; tiles whose window the grid border clips get a larger radius
+    // (same staged area): their queries need a wider search for the same K (one-sided neighbourhoods)
     const int ly0 = ty * kKnnTileH, ly1 = min(ly0 + kKnnTileH - 1, g.Hq - 1);
     const int lx0 = tx * kKnnTileW, lx1 = min(lx0 + kKnnTileW - 1, g.Wq - 1);
-    const int wy0 = max(min((int)floorf(((float)(ly0 * g.s) + g.off) * g.inv_cs), g.Hc - 1) - r, 0);
-    const int wy1 = min(min((int)floorf(((float)(ly1 * g.s) + g.off) * g.inv_cs), g.Hc - 1) + r, g.Hc - 1);
-    const int wx0 = max(min((int)floorf(((float)(lx0 * g.s) + g.off) * g.inv_cs), g.Wc - 1) - r, 0);
-    const int wx1 = min(min((int)floorf(((float)(lx1 * g.s) + g.off) * g.inv_cs), g.Wc - 1) + r, g.Wc - 1);
+    const int cy_lo = min((int)floorf(((float)(ly0 * g.s) + g.off) * g.inv_cs), g.Hc - 1);
+    const int cy_hi = min((int)floorf(((float)(ly1 * g.s) + g.off) * g.inv_cs), g.Hc - 1);
+    const int cx_lo = min((int)floorf(((float)(lx0 * g.s) + g.off) * g.inv_cs), g.Wc - 1);
+    const int cx_hi = min((int)floorf(((float)(lx1 * g.s) + g.off) * g.inv_cs), g.Wc - 1);
+    int r = g.r_fast;
+    {
+        const int full = (cy_hi - cy_lo + 1 + 2 * r) * (cx_hi - cx_lo + 1 + 2 * r);
+        while (r < 10) {
+            const int nr2 = min(cy_hi + r + 1, g.Hc - 1) - max(cy_lo - r - 1, 0) + 1;
+            const int nc2 = min(cx_hi + r + 1, g.Wc - 1) - max(cx_lo - r - 1, 0) + 1;
+            if (nr2 * nc2 > full) break;
+            if (nr2 == g.Hc && nc2 == g.Wc) { r = 10; break; }     // whole grid staged already
+            ++r;
+        }
+    }
+    const int wy0 = max(cy_lo - r, 0), wy1 = min(cy_hi + r, g.Hc - 1);
+    const int wx0 = max(cx_lo - r, 0), wx1 = min(cx_hi + r, g.Wc - 1);
     const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 1;
 
     if (tid == 0) blk_max = 0u;
     if (tid < 32) {                                   // row run lengths -> exclusive scan
         int len = 0;
         if (tid < nrow)
-            len = __ldg(cstart + (wy0 + tid) * g.Wc + wx1 + 1) - __ldg(cstart + (wy0 + tid) * g.Wc + wx0);
+            len = __ldg(cstart + (wy0 + tid) * g.Wc + wx1 + 1) - __ldg(cstart + (wy0 + tid) * g.Wc + wx0) + kRowPad;
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -353,15 +410,19 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
         for (int lr = tid >> 5; lr < nrow; lr += kKnnBlock / 32) {
             const int *crow = cstart + (wy0 + lr) * g.Wc + wx0;
             const int ga = __ldg(crow);
-            const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base;
+            const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base - kRowPad;
             for (int lc = lane; lc <= ncol; lc += 32)
                 s_cell[lr][lc] = (unsigned short)min(__ldg(crow + lc) - ga + base, kStageCap);
-            for (int k = lane; k < len; k += 32) {
-                const float4 rec = __ldg(sorted + ga + k);
-                s_py[base + k] = rec.x;
-                s_px[base + k] = rec.y;
-                s_pj[base + k] = __float_as_int(rec.z);
-                if (FUSED) s_fl[base + k] = __ldg(sfl + ga + k);
+            for (int k = lane; k < len + kRowPad; k += 32) {
+                if (k < len) {
+                    const float4 rec = __ldg(sorted + ga + k);
+                    s_pt[base + k] = make_rec(rec.x, rec.y, FUSED ? __ldg(sfl + ga + k) : make_float2(0.f, 0.f),
+                                              (Rec *)nullptr);
+                    s_pj[base + k] = __float_as_int(rec.z);
+                } else {                                   // sentinel: infinitely far, never listed
+                    s_pt[base + k] = make_rec(1e30f, 1e30f, make_float2(0.f, 0.f), (Rec *)nullptr);
+                    s_pj[base + k] = 0x7fffffff;
+                }
             }
         }
     }
@@ -375,17 +436,22 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
     int t_j = 0;
     float ay = 0.0f, ax = 0.0f;
     int m = 0, need = 0;
+    int miss = 0;      // 0 window not staged, 1 no bracket, 2 / 3 too few / many points, 4 K-th beyond, 5 list full,
+                       // 6 previous-bin bracket missed
+    bool had_guess = false;
+    float guess = 0.0f;
     if (active && staged) {
         const float qy = __fadd_rn((float)(iy * g.s), g.off);
         const float qx = __fadd_rn((float)(ix * g.s), g.off);
         const int cqy = min((int)floorf(qy * g.inv_cs), g.Hc - 1);
         const int cqx = min((int)floorf(qx * g.inv_cs), g.Wc - 1);
         const float bnd = window_bound(cqy, cqx, r, g, qy, qx);
-        auto list_d = [&](int u) {                      // distance of list entry u, recomputed
-            const int i = s_li[u][tid] & 0x3ff;
-            const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
+        auto dist_at = [&](int i) {
+            const Rec pt = s_pt[i];
+            const float dy = __fsub_rn(qy, pt.x), dx = __fsub_rn(qx, pt.y);
             return L1D ? __fadd_rn(fabsf(dy), fabsf(dx)) : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
         };
+        auto list_d = [&](int u) { return dist_at(s_li[u][tid] & 0x3ff); };   // recomputed on demand
         // Columns of window row `lr` that can hold a point with d < hi: the row's cells are clipped
         // to the disc (l1: diamond) of that radius around the query - about half of the square
         // window.  Conservative by 1e-5 relative, like window_bound: cells are assigned with a
@@ -405,58 +471,67 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
             e = s_cell[lr][c1];
             return true;
         };
+        // window rows / columns (relative to the staged window) whose cells can hold a point with
+        // d < hi: closed form, conservative by 1e-4 relative + 1e-3 px (cells are assigned with a
+        // rounded product); hi <= bnd keeps it inside the staged window, the clamps are for safety
+        auto extent = [&](float hi, int &r0w, int &r1w, int &c0w, int &c1w) {
+            const float sq = (L1D ? hi : approx_sqrt(hi)) * (1.0f + 1e-4f) + 1e-3f;
+            const float fr0 = fmaxf(floorf((qy - sq) * g.inv_cs), (float)wy0);
+            const float fr1 = fminf(floorf((qy + sq) * g.inv_cs), (float)wy1);
+            const float fc0 = fmaxf(floorf((qx - sq) * g.inv_cs), (float)wx0);
+            const float fc1 = fminf(floorf((qx + sq) * g.inv_cs), (float)wx1);
+            r0w = (int)fr0 - wy0;
+            r1w = (int)fr1 - wy0;
+            c0w = (int)fc0 - wx0;
+            c1w = (int)fc1 - wx0 + 1;
+        };
         if (GUESS) {
             // K-th key of the same cell in the previous bin as left by the *fast* kernel (NaN where
             // it was not settled there - then a direct neighbour's value serves as the guess)
             const float *tp = tau + sq - g.q;
-            float tprev = __ldcg(tp);
-            if (!(tprev == tprev) && ix > 0) tprev = __ldcg(tp - 1);
-            if (!(tprev == tprev) && ix + 1 < g.Wq) tprev = __ldcg(tp + 1);
-            if (!(tprev == tprev) && iy > 0) tprev = __ldcg(tp - g.Wq);
-            if (!(tprev == tprev) && iy + 1 < g.Hq) tprev = __ldcg(tp + g.Wq);
-            const float pred = tprev;
+            float tprev = __ldcg(tp);                              // unsettled cells hold NaN or -guess
+            if (!(tprev >= 0.0f) && ix > 0) tprev = __ldcg(tp - 1);
+            if (!(tprev >= 0.0f) && ix + 1 < g.Wq) tprev = __ldcg(tp + 1);
+            if (!(tprev >= 0.0f) && iy > 0) tprev = __ldcg(tp - g.Wq);
+            if (!(tprev >= 0.0f) && iy + 1 < g.Hq) tprev = __ldcg(tp + g.Wq);
+            const float pred = tprev >= 0.0f ? tprev : __int_as_float(0x7fc00000);
+            guess = pred;
             const float lo = kGuessLo * pred;
             const float hi = fminf(kGuessHi * pred, bnd);
+            had_guess = pred == pred;
+            miss = 6;                                          // had a guess, the bracket missed
             if (hi > lo) {
-                int rt = 0;                                    // smallest window holding every d < hi
-                while (rt < r && window_bound(cqy, cqx, rt, g, qy, qx) < hi) ++rt;
-                const int r0w = max(cqy - rt, 0) - wy0, r1w = min(cqy + rt, g.Hc - 1) - wy0;
-                const int c0w = max(cqx - rt, 0) - wx0, c1w = min(cqx + rt, g.Wc - 1) - wx0 + 1;
+                int r0w, r1w, c0w, c1w;
+                extent(hi, r0w, r1w, c0w, c1w);
                 int below = 0;
                 const float invw = 7.0f / (hi - lo);
                 unsigned hlo = 0u, hhi = 0u;                   // 7 bracket slices x 8-bit counters
-                auto visit = [&](float d, int i) {
-                    if (d < lo) {
-                        ++below;
-                        if (FUSED) {
-                            const float2 f = s_fl[i];
-                            ay = __fadd_rn(ay, f.x);
-                            ax = __fadd_rn(ax, f.y);
-                        }
-                    } else if (d < hi) {
-                        if (m < kListCap) s_li[m][tid] = (unsigned short)i;
-                        ++m;
-                    }
-                };
-                auto dist_at = [&](int i) {
-                    const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
-                    return L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
-                               : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
-                };
+                const unsigned lp0 = (unsigned)__cvta_generic_to_shared(&s_li[0][tid]);
+                const unsigned lp_full = lp0 + (kListCap - 3) * (kKnnBlock * 2);   // no room for 4 more
+                unsigned lp = lp0;
+                bool overflow = false;
                 for (int lr = r0w; lr <= r1w; ++lr) {
                     int a, e;
                     if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
-                    int i = a;
-                    for (; i + 4 <= e; i += 4) {          // distances first (4 loads in flight)
-                        const float d0 = dist_at(i), d1 = dist_at(i + 1), d2 = dist_at(i + 2),
-                                    d3 = dist_at(i + 3);
-                        visit(d0, i);
-                        visit(d1, i + 1);
-                        visit(d2, i + 2);
-                        visit(d3, i + 3);
+                    // groups of four records; the ones past `e` are further points of the same
+                    // row or its sentinels - legitimate candidates, never counted twice
+                    for (int i = a; i < e; i += 4) {
+                        if (lp >= lp_full) { overflow = true; break; }
+                        const Rec p0 = s_pt[i], p1 = s_pt[i + 1], p2 = s_pt[i + 2], p3 = s_pt[i + 3];
+#define CMAX_DIST(P) (L1D ? __fadd_rn(fabsf(__fsub_rn(qy, P.x)), fabsf(__fsub_rn(qx, P.y)))            \
+                          : __fadd_rn(__fmul_rn(__fsub_rn(qy, P.x), __fsub_rn(qy, P.x)),               \
+                                      __fmul_rn(__fsub_rn(qx, P.y), __fsub_rn(qx, P.y))))
+                        const float d0 = CMAX_DIST(p0), d1 = CMAX_DIST(p1), d2 = CMAX_DIST(p2), d3 = CMAX_DIST(p3);
+#undef CMAX_DIST
+                        classify<FUSED>(d0, lo, hi, rec_flow(p0), i, below, ay, ax, lp);
+                        classify<FUSED>(d1, lo, hi, rec_flow(p1), i + 1, below, ay, ax, lp);
+                        classify<FUSED>(d2, lo, hi, rec_flow(p2), i + 2, below, ay, ax, lp);
+                        classify<FUSED>(d3, lo, hi, rec_flow(p3), i + 3, below, ay, ax, lp);
                     }
-                    for (; i < e; ++i) visit(dist_at(i), i);
+                    if (overflow) break;
                 }
+                m = (int)((lp - lp0) / (kKnnBlock * 2));
+                if (overflow) m = kListCap + 1;
                 // slice the listed candidates (kept out of the hot loop: nearly every warp
                 // iteration has *some* lane inside the bracket)
                 for (int u = 0; u < min(m, kListCap); ++u) {
@@ -482,7 +557,7 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                         const int bk = pk >> 10, i = pk & 0x3ff;
                         if (bk < bstar) {
                             if (FUSED) {
-                                const float2 f = s_fl[i];
+                                const float2 f = rec_flow(s_pt[i]);
                                 ay = __fadd_rn(ay, f.x);
                                 ax = __fadd_rn(ax, f.y);
                             }
@@ -496,34 +571,47 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                     resolved = true;
                 }
             }
-        } else {
-            const int r0w = max(cqy - r, 0) - wy0, r1w = min(cqy + r, g.Hc - 1) - wy0;
-            const int c0w = max(cqx - r, 0) - wx0, c1w = min(cqx + r, g.Wc - 1) - wx0 + 1;
+        }
+        // GUESS = false: the self-contained histogram select.  (Measured: running it as a second
+        // chance inside the GUESS kernels for cells whose bracket missed costs 0.17 - 0.33 ms per
+        // DSEC batch in divergence, far more than the work-list kernel needs for them.)  Pass 1 counts the candidates below
+        // `lo` and in seven slices of [lo, hi); when the K-th key lies beyond `hi` (sparse, one-sided
+        // neighbourhoods at the image border, where a density estimate is far off) the bracket moves
+        // up, when one slice holds more candidates than the list takes it narrows to that slice.
+        // Pass 2 accumulates the sure members and lists the slice.
+        if (!GUESS) {
+            // density-based estimate of the K-th key (points of the nominal window) and the
+            // histogram bracket around it
+            const int re = min(r, g.r_fast);
+            const int e_r0 = max(cqy - re, 0) - wy0, e_r1 = min(cqy + re, g.Hc - 1) - wy0;
+            const int e_c0 = max(cqx - re, 0) - wx0, e_c1 = min(cqx + re, g.Wc - 1) - wx0 + 1;
             int nwin = 0;
-            for (int lr = r0w; lr <= r1w; ++lr) nwin += s_cell[lr][c1w] - s_cell[lr][c0w];
-            // density-based estimate of the K-th key and the histogram bracket around it
-            const float area = (float)((r1w - r0w + 1) * (c1w - c0w)) * g.cs * g.cs;
+            for (int lr = e_r0; lr <= e_r1; ++lr) nwin += s_cell[lr][e_c1] - s_cell[lr][e_c0];
+            const float area = (float)((e_r1 - e_r0 + 1) * (e_c1 - e_c0)) * g.cs * g.cs;
             float est = (float)g.K * area / (3.14159265f * (float)max(nwin, 1));
             if (L1D) est = sqrtf(est * 1.5707963f);        // l1 ball of radius t has area 2 t^2
-            const float lo = 0.45f * est;
-            const float hi = fminf(1.7f * est, bnd);
-            if (nwin >= g.K && nwin <= 255 && hi > lo) {
+            float lo = 0.45f * est;
+            float hi = fminf(1.7f * est, bnd);
+            miss = 1;
+            for (int attempt = 0; attempt < 5 && hi > lo; ++attempt) {
                 const float invw = 7.0f / (hi - lo);
+                int r0w, r1w, c0w, c1w;
+                extent(hi, r0w, r1w, c0w, c1w);
                 // ---- pass 1: histogram ---------------------------------------------------------
                 unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit
+                int seen = 0;
                 for (int lr = r0w; lr <= r1w; ++lr) {
                     int a, e;
                     if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
+                    seen += e - a;
                     for (int i = a; i < e; ++i) {
-                        const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
-                        const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
-                                            : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
-                        const int bk = bucket_of(d, lo, invw);
+                        const int bk = bucket_of(dist_at(i), lo, invw);
                         const unsigned inc = 1u << ((bk & 3) << 3);
                         hlo += bk < 4 ? inc : 0u;
                         hhi += (bk >= 4 && bk < 8) ? inc : 0u;
                     }
                 }
+                if (seen > 255) { miss = 3; break; }      // the packed counters could have wrapped
                 int bstar = -1, below = 0, in_b = 0, cum = 0;
 #pragma unroll
                 for (int bk = 0; bk < 8; ++bk) {
@@ -531,31 +619,52 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                     if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; in_b = cb; }
                     cum += cb;
                 }
-                if (bstar >= 0 && in_b <= kListCap) {
-                    // ---- pass 2: accumulate sure members, collect the boundary bucket ------------
-                    for (int lr = r0w; lr <= r1w; ++lr) {
-                        int a, e;
-                        if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
-                        for (int i = a; i < e; ++i) {
-                            const float dy = __fsub_rn(qy, s_py[i]), dx = __fsub_rn(qx, s_px[i]);
-                            const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
-                                                : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
-                            const int bk = bucket_of(d, lo, invw);
-                            if (bk < bstar) {
-                                if (FUSED) {
-                                    const float2 f = s_fl[i];
-                                    ay = __fadd_rn(ay, f.x);
-                                    ax = __fadd_rn(ax, f.y);
-                                }
-                            } else if (bk == bstar) {
-                                s_li[m][tid] = (unsigned short)i;
-                                ++m;
+                if (bstar < 0) {                          // K-th key beyond hi: move the bracket up
+                    miss = 4;
+                    if (!(hi < bnd)) break;
+                    lo = hi;
+                    hi = fminf(3.0f * hi, bnd);
+                    continue;
+                }
+                if (bstar == 0) {                         // K-th key below lo: move the bracket down
+                    miss = 1;
+                    hi = lo;
+                    lo = 0.25f * lo;
+                    continue;
+                }
+                if (in_b > kListCap) {                    // crowded slice: narrow the bracket to it
+                    miss = 5;
+                    const float w = (hi - lo) * (1.0f / 7.0f);
+                    const float nlo = lo + (float)(bstar - 1) * w * 0.999f, nhi = lo + (float)bstar * w * 1.001f;
+                    lo = nlo;
+                    hi = fminf(nhi, hi);
+                    continue;
+                }
+                // ---- pass 2: accumulate sure members, collect the boundary bucket ------------
+                for (int lr = r0w; lr <= r1w; ++lr) {
+                    int a, e;
+                    if (!row_span(lr, hi, c0w, c1w, a, e)) continue;
+                    for (int i = a; i < e; ++i) {
+                        const Rec pt = s_pt[i];
+                        const float dy = __fsub_rn(qy, pt.x), dx = __fsub_rn(qx, pt.y);
+                        const float d = L1D ? __fadd_rn(fabsf(dy), fabsf(dx))
+                                            : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+                        const int bk = bucket_of(d, lo, invw);
+                        if (bk < bstar) {
+                            if (FUSED) {
+                                const float2 f = rec_flow(pt);
+                                ay = __fadd_rn(ay, f.x);
+                                ax = __fadd_rn(ax, f.y);
                             }
+                        } else if (bk == bstar) {
+                            s_li[m][tid] = (unsigned short)i;
+                            ++m;
                         }
                     }
-                    need = g.K - below;
-                    resolved = true;
                 }
+                need = g.K - below;
+                resolved = true;
+                break;
             }
         }
         if (resolved) {
@@ -578,7 +687,7 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                     s_li[t][tid] = (unsigned short)ib;
                 }
                 if (FUSED) {
-                    const float2 f = s_fl[ib];
+                    const float2 f = rec_flow(s_pt[ib]);
                     ay = __fadd_rn(ay, f.x);
                     ax = __fadd_rn(ax, f.y);
                 }
@@ -600,8 +709,11 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                 if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
             }
         } else {
-            tau[sq] = __int_as_float(0x7fc00000);              // NaN: settled later by the heap kernel
+            // unsettled: NaN, or minus the guess that failed (the work-list kernel centres its search
+            // on it); settled later by the work-list kernels
+            tau[sq] = (had_guess && guess > 0.0f) ? -guess : __int_as_float(0x7fc00000);
             worklist[atomicAdd(work_count, 1)] = (int)sq;
+            atomicAdd(work_count + 1 + miss, 1);               // inspection: why the fast path gave up
         }
     }
     __syncthreads();
@@ -712,6 +824,174 @@ knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__re
             reinterpret_cast<float2 *>(lut)[sq] = v;
             if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3b. work-list queries, first resort: one WARP per query, histogram select over the global cell list
+// ---------------------------------------------------------------------------------------------
+// The cells the staged kernel gives up on are the ones whose K-th key moved out of the bracket of
+// the previous bin: sparse, one-sided neighbourhoods at the image border, a few dozen per slab.
+// A per-thread ring walk (knn_heap_kernel) runs them at 3 active lanes per warp instruction; here
+// the 32 lanes share the candidates of one query instead: pass 1 = per-lane packed histogram of
+// the distances around the failed guess (or a nominal-density estimate), reduced with REDUX; the
+// bracket moves up / down / narrows until one slice of at most 32 candidates holds the K-th key;
+// pass 2 = lanes add the flows of the sure members, the slice is compacted with ballots and ranked
+// by (distance, index) with shuffles.  Exact; whatever it cannot settle goes to knn_heap_kernel.
+template <bool L1D>
+__global__ void __launch_bounds__(kKnnBlock)
+knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
+                const float2 *__restrict__ sflow_all, float *__restrict__ tau, int *__restrict__ jcut,
+                unsigned *__restrict__ tau_max, unsigned *__restrict__ tile_max,
+                const int *__restrict__ worklist, const int *__restrict__ work_count, int fused,
+                float *__restrict__ lut, float *__restrict__ lut_copy, int *__restrict__ worklist2,
+                int *__restrict__ work_count2)
+{
+    __shared__ float s_d[kKnnBlock / 32][32];
+    __shared__ int s_j[kKnnBlock / 32][32], s_i[kKnnBlock / 32][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int total = work_count[0];
+    const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
+    const int tiles = tiles_x * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
+    const float tau_nom = (float)g.K * (float)g.H * (float)g.W / (3.14159265f * (float)g.n);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int w = blockIdx.x * (kKnnBlock / 32) + wid; w < total; w += gridDim.x * (kKnnBlock / 32)) {
+        const int64_t sq = worklist[w];
+        const int64_t slab = sq / g.q;
+        const Query q = make_query((int)(sq - slab * g.q), g);
+        const int *cstart = cell_start + slab * (g.NC + 1);
+        const float4 *sorted = sorted_all + slab * g.n;
+        const float2 *sfl = fused ? sflow_all + slab * g.n : nullptr;
+        const float t0 = tau[sq];
+        float est = t0 < 0.0f ? -t0 : (L1D ? sqrtf(tau_nom * 1.5707963f) : tau_nom);
+        float lo = 0.45f * est, hi = 1.7f * est;
+        bool done = false;
+        for (int attempt = 0; attempt < 8 && !done; ++attempt) {
+            const float invw = 7.0f / (hi - lo);
+            // rows / columns of cells that can hold a point with d < hi (conservative, see knn_fast_kernel)
+            const float sqr = (L1D ? hi : approx_sqrt(hi)) * (1.0f + 1e-4f) + 1e-3f;
+            const int r0 = (int)fminf(fmaxf(floorf((q.qy - sqr) * g.inv_cs), 0.0f), (float)(g.Hc - 1));
+            const int r1 = (int)fminf(fmaxf(floorf((q.qy + sqr) * g.inv_cs), 0.0f), (float)(g.Hc - 1));
+            const int c0 = (int)fminf(fmaxf(floorf((q.qx - sqr) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
+            const int c1 = (int)fminf(fmaxf(floorf((q.qx + sqr) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
+            const bool whole = r0 == 0 && c0 == 0 && r1 == g.Hc - 1 && c1 == g.Wc - 1;
+            // ---- pass 1 ------------------------------------------------------------------------
+            unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit per lane
+            int mine = 0;
+            for (int row = r0; row <= r1; ++row) {
+                const int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
+                for (int i = a + lane; i < e; i += 32) {
+                    const float4 rec = __ldg(sorted + i);
+                    const int bk = bucket_of(knn_dist(q.qy, q.qx, rec.x, rec.y, L1D), lo, invw);
+                    const unsigned inc = 1u << ((bk & 3) << 3);
+                    hlo += bk < 4 ? inc : 0u;
+                    hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                    ++mine;
+                }
+            }
+            if (__any_sync(0xffffffffu, mine > 255)) break;       // packed counters could have wrapped
+            int bstar = -1, below = 0, in_b = 0, cum = 0;
+#pragma unroll
+            for (int bk = 0; bk < 8; ++bk) {
+                const unsigned mineb = ((bk < 4 ? hlo : hhi) >> ((bk & 3) << 3)) & 0xffu;
+                const int cb = (int)__reduce_add_sync(0xffffffffu, mineb);
+                if (bstar < 0 && cum + cb >= g.K) { bstar = bk; below = cum; in_b = cb; }
+                cum += cb;
+            }
+            if (bstar < 0) {                              // K-th key beyond hi
+                if (whole) break;                         // (cannot happen: n >= K)
+                lo = hi;
+                hi = 3.0f * hi;
+                continue;
+            }
+            if (bstar == 0) {                             // K-th key below lo
+                hi = lo;
+                lo = 0.25f * lo;
+                if (!(hi > lo)) break;
+                continue;
+            }
+            if (in_b > 32) {                              // crowded slice: narrow the bracket to it
+                const float wdt = (hi - lo) * (1.0f / 7.0f);
+                const float nlo = lo + (float)(bstar - 1) * wdt * 0.999f, nhi = lo + (float)bstar * wdt * 1.001f;
+                if (!(nhi - nlo < hi - lo)) break;
+                lo = nlo;
+                hi = fminf(nhi, hi);
+                continue;
+            }
+            // ---- pass 2: sure members and the slice ---------------------------------------------
+            float ay = 0.0f, ax = 0.0f;
+            int base = 0;
+            for (int row = r0; row <= r1; ++row) {
+                const int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
+                for (int i0 = a; i0 < e; i0 += 32) {       // warp-uniform trip count (ballots inside)
+                    const int i = i0 + lane;
+                    int bk = 8;
+                    float d = 0.0f;
+                    int j = 0;
+                    if (i < e) {
+                        const float4 rec = __ldg(sorted + i);
+                        d = knn_dist(q.qy, q.qx, rec.x, rec.y, L1D);
+                        j = __float_as_int(rec.z);
+                        bk = bucket_of(d, lo, invw);
+                        if (fused && bk < bstar) {
+                            const float2 f = __ldg(sfl + i);
+                            ay = __fadd_rn(ay, f.x);
+                            ax = __fadd_rn(ax, f.y);
+                        }
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, bk == bstar);
+                    if (bk == bstar) {
+                        const int pos = base + __popc(hit & lt_mask);
+                        s_d[wid][pos] = d;
+                        s_j[wid][pos] = j;
+                        s_i[wid][pos] = i;
+                    }
+                    base += __popc(hit);
+                }
+            }
+            __syncwarp();
+            // rank the slice by (distance, index): lane l owns candidate l
+            const int need = g.K - below;                  // 1 <= need <= in_b <= 32
+            const bool have = lane < in_b;
+            const float md = have ? s_d[wid][lane] : INFINITY;
+            const int mj = have ? s_j[wid][lane] : 0x7fffffff;
+            int rank = 0;
+            for (int u = 0; u < in_b; ++u) {
+                const float du = __shfl_sync(0xffffffffu, md, u);
+                const int ju = __shfl_sync(0xffffffffu, mj, u);
+                rank += lex_less(du, ju, md, mj) ? 1 : 0;
+            }
+            if (fused && have && rank < need) {
+                const float2 f = __ldg(sfl + s_i[wid][lane]);
+                ay = __fadd_rn(ay, f.x);
+                ax = __fadd_rn(ax, f.y);
+            }
+            const unsigned kth = __ballot_sync(0xffffffffu, have && rank == need - 1);
+            const int src = __ffs(kth) - 1;
+            const float t_d = __shfl_sync(0xffffffffu, md, src);
+            const int t_j = __shfl_sync(0xffffffffu, mj, src);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {             // fixed tree order: deterministic
+                ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, o));
+                ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, o));
+            }
+            if (lane == 0) {
+                tau[sq] = t_d;
+                jcut[sq] = t_j;
+                const unsigned bits = __float_as_uint(t_d);
+                atomicMax(tau_max + slab, bits);
+                atomicMax(tile_max + slab * tiles + (q.iy / kKnnTileH) * tiles_x + q.ix / kKnnTileW, bits);
+                if (fused) {
+                    const float Kf = (float)g.K;
+                    const float2 v = make_float2(__fdiv_rn(ay, Kf), __fdiv_rn(ax, Kf));
+                    reinterpret_cast<float2 *>(lut)[sq] = v;
+                    if (lut_copy) reinterpret_cast<float2 *>(lut_copy)[sq] = v;
+                }
+            }
+            __syncwarp();
+            done = true;
+        }
+        if (!done && lane == 0) worklist2[atomicAdd(work_count2, 1)] = (int)sq;
     }
 }
 
@@ -894,118 +1174,377 @@ lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *_
 // ---------------------------------------------------------------------------------------------
 // dtraj[b, r, j]      =  sum_bins sum_{c : j in KNN(b,bin,c)} w(c,j) dLUT[b,bin,c,r]
 // dtraj[b, R+bin, j]  = -sum_r (same inner sum) [- / + the flow_to_next terms]
-// Stage A: one thread per (sample, bin, trajectory) gathers this bin's contribution;
-// stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
-// fixed order -> deterministic, and 15x more threads in flight for the latency-bound gather.
-template <bool L1D, bool IWD, bool F2N, int RT>   // RT = compile-time R (1) or 0 = runtime R
-__global__ void __launch_bounds__(64, RT == 1 ? 24 : 12)
-lut_backward_kernel(const float *__restrict__ traj, Geom g, const float *__restrict__ tau,
-                    const int *__restrict__ jcut, const float *__restrict__ wsum,
-                    const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
-                    const float *__restrict__ dlut, const float *__restrict__ df2n,
-                    float2 *__restrict__ part)
+// Stage A (lut_backward_tile_kernel): one CTA per (tile of 8x16 cell-list cells, bin, sample), one
+// thread per trajectory point of the tile (the points come out of the forward's cell list, so the
+// threads of a CTA are spatial neighbours).  The LUT cells such a point can be a K-neighbour of form
+// a *regular lattice window* around the tile: their (tau, jcut) keys and dLUT values are staged in
+// shared memory once, together with the per-row maximum of tau, and every thread walks its rows of
+// the lattice with the same short, convergent loop.  Membership is `key(c, j) <= (tau_c, jcut_c)`
+// re-evaluated with bit-identical distance arithmetic.  Points the tile rectangle does not really
+// contain (cell_of clamps out-of-grid points into the border cells) and tiles whose reach window
+// exceeds the staging capacity take gather_generic, the global-memory walk of the same lattice.
+// Stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
+// fixed order -> deterministic.
+constexpr int kBwdTileW = 16;                     // cell-list cells per CTA: TH x 16
+constexpr int kBwdWinCap = 1280;                  // staged LUT cells per CTA (incl. row padding)
+constexpr int kBwdMaxRows = 64;
+
+template <bool L1D, bool IWD, bool F2N, int RT>
+struct BwdAcc {
+    float2 binr[RT ? RT : kMaxTref];
+    float2 nxt;
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int r = 0; r < (RT ? RT : kMaxTref); ++r) binr[r] = make_float2(0.f, 0.f);
+        nxt = make_float2(0.f, 0.f);
+    }
+};
+
+// global-memory walk of the lattice around p (any reach, any position); order = rows, then columns
+struct LatticeGeom {            // the few Geom fields gather_generic needs, passed in registers
+    int Hq, Wq, s, R, nb, q;
+    float off;
+};
+
+template <bool L1D, bool IWD, bool F2N, int RT>
+__device__ __noinline__ void gather_generic(const LatticeGeom g, int slab, int b, int bin, int j, float2 p,
+                                            const float *__restrict__ tau, const int *__restrict__ jcut,
+                                            const float *__restrict__ wsum,
+                                            const unsigned *__restrict__ tau_max,
+                                            const unsigned *__restrict__ tile_max,
+                                            const float *__restrict__ dlut, const float *__restrict__ df2n,
+                                            BwdAcc<L1D, IWD, F2N, RT> &acc)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int bin = blockIdx.y;
-    const int b = blockIdx.z;
-    if (j >= g.n) return;
     const int R = RT ? RT : g.R;
-    const float invK = 1.0f / (float)g.K;
     const float fs = (float)g.s, inv_s = 1.0f / fs;
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
     const int tiles_y = (g.Hq + kKnnTileH - 1) / kKnnTileH;
     const int Wq = g.Wq;
-    const int slab = b * g.nb + bin;
-    const float2 p = slab_points(traj, g, slab)[j];
     const float tm = __uint_as_float(__ldg(tau_max + slab));
     float rho_g = L1D ? tm : approx_sqrt(tm);
     rho_g = rho_g * 1.0001f + 1e-3f;
-    float2 nxt = make_float2(0.f, 0.f);
-    float2 binr[RT ? RT : kMaxTref];
-#pragma unroll
-    for (int r = 0; r < (RT ? RT : kMaxTref); ++r) binr[r] = make_float2(0.f, 0.f);
     const float *tau_s = tau + (int64_t)slab * g.q;
     const int *jcut_s = jcut + (int64_t)slab * g.q;
     const float2 *dl_s = reinterpret_cast<const float2 *>(dlut) + (int64_t)slab * g.q * g.R;
     const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
                              : nullptr;
     const bool do_next = F2N && bin < g.nb - 1;
-    if (p.x == p.x && p.y == p.y && rho_g == rho_g) {
-        // local reach: the largest tau of any 16x8-query tile that can contain a query whose
-        // K-set holds p (tile rectangle closer to p than the tile's own reach)
-        const int ty0 = max(0, (int)floorf((p.x - rho_g - g.off) * inv_s)) / kKnnTileH;
-        const int ty1 = min(g.Hq - 1, max(0, (int)ceilf((p.x + rho_g - g.off) * inv_s))) / kKnnTileH;
-        const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
-        const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
-        const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
-        // a tile matters when its rectangle is closer to p than its own reach; compared on the
-        // tau scale itself (squared distance for l2) with a relative + absolute margin, so the
-        // loop needs no square root - one at the end gives the search radius
-        float tbest = -1.0f;
-        for (int ty = ty0; ty <= ty1; ++ty) {
-            const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
-            const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
-            const float ddy = fmaxf(fmaxf(y_lo - p.x, p.x - y_hi), 0.0f);
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
-                const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
-                const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
-                const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
-                const float gap = L1D ? ddy + ddx : ddy * ddy + ddx * ddx;
-                if (gap <= tmt * 1.001f + 1e-2f) tbest = fmaxf(tbest, tmt);
-            }
+    if (!(p.x == p.x && p.y == p.y && rho_g == rho_g)) return;
+    // local reach: the largest tau of any 16x8-query tile that can contain a query whose
+    // K-set holds p (tile rectangle closer to p than the tile's own reach)
+    const int ty0 = max(0, (int)floorf((p.x - rho_g - g.off) * inv_s)) / kKnnTileH;
+    const int ty1 = min(g.Hq - 1, max(0, (int)ceilf((p.x + rho_g - g.off) * inv_s))) / kKnnTileH;
+    const int tx0 = max(0, (int)floorf((p.y - rho_g - g.off) * inv_s)) / kKnnTileW;
+    const int tx1 = min(Wq - 1, max(0, (int)ceilf((p.y + rho_g - g.off) * inv_s))) / kKnnTileW;
+    const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
+    // a tile matters when its rectangle is closer to p than its own reach; compared on the
+    // tau scale itself (squared distance for l2) with a relative + absolute margin, so the
+    // loop needs no square root - one at the end gives the search radius
+    float tbest = -1.0f;
+    for (int ty = ty0; ty <= ty1; ++ty) {
+        const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
+        const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
+        const float ddy = fmaxf(fmaxf(y_lo - p.x, p.x - y_hi), 0.0f);
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
+            const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
+            const float ddx = fmaxf(fmaxf(x_lo - p.y, p.y - x_hi), 0.0f);
+            const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
+            const float gap = L1D ? ddy + ddx : ddy * ddy + ddx * ddx;
+            if (gap <= tmt * 1.001f + 1e-2f) tbest = fmaxf(tbest, tmt);
         }
-        const float rho = tbest < 0.0f ? 0.0f : (L1D ? tbest : approx_sqrt(tbest)) * 1.0001f + 1e-3f;
-        const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
-        const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
-        const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
-        const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
-        for (int iy = iy0; iy <= iy1 && ix0 <= ix1; ++iy) {
-            const float qy = __fadd_rn((float)(iy * g.s), g.off);
-            const float dy = __fsub_rn(qy, p.x);
-            const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
-            // clip the row to the reach disc (l1: diamond); conservative by one cell
-            const float hx = L1D ? rho - fabsf(dy) : approx_sqrt(fmaxf(rho * rho - dy * dy, 0.0f)) * 1.0001f + 1e-3f;
-            const int jx0 = max(ix0, (int)floorf((p.y - hx - g.off) * inv_s));
-            const int jx1 = min(ix1, (int)ceilf((p.y + hx - g.off) * inv_s));
-            const int nx = jx1 - jx0 + 1;
-            const int o = iy * Wq + jx0;
-            const float *tp = tau_s + o;
-            float qx = __fadd_rn((float)(jx0 * g.s), g.off);   // exact: multiples of 0.5
-#pragma unroll 4
-            for (int k = 0; k < nx; ++k, qx += fs) {
-                const float dx = __fsub_rn(qx, p.y);
-                const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
-                const float tc = __ldg(tp + k);
-                if (d <= tc) {
-                    if (d < tc || j <= __ldg(jcut_s + o + k)) {
-                        float w = 1.0f;
-                        if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
-                                                __ldg(wsum + (int64_t)slab * g.q + o + k));
+    }
+    const float rho = tbest < 0.0f ? 0.0f : (L1D ? tbest : approx_sqrt(tbest)) * 1.0001f + 1e-3f;
+    const int iy0 = max(0, (int)floorf((p.x - rho - g.off) * inv_s));
+    const int iy1 = min(g.Hq - 1, (int)ceilf((p.x + rho - g.off) * inv_s));
+    const int ix0 = max(0, (int)floorf((p.y - rho - g.off) * inv_s));
+    const int ix1 = min(Wq - 1, (int)ceilf((p.y + rho - g.off) * inv_s));
+    for (int iy = iy0; iy <= iy1 && ix0 <= ix1; ++iy) {
+        const float qy = __fadd_rn((float)(iy * g.s), g.off);
+        const float dy = __fsub_rn(qy, p.x);
+        const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
+        // clip the row to the reach disc (l1: diamond); conservative by one cell
+        const float hx = L1D ? rho - fabsf(dy) : approx_sqrt(fmaxf(rho * rho - dy * dy, 0.0f)) * 1.0001f + 1e-3f;
+        const int jx0 = max(ix0, (int)floorf((p.y - hx - g.off) * inv_s));
+        const int jx1 = min(ix1, (int)ceilf((p.y + hx - g.off) * inv_s));
+        const int nx = jx1 - jx0 + 1;
+        const int o = iy * Wq + jx0;
+        const float *tp = tau_s + o;
+        float qx = __fadd_rn((float)(jx0 * g.s), g.off);   // exact: multiples of 0.5
+        for (int k = 0; k < nx; ++k, qx += fs) {
+            const float dx = __fsub_rn(qx, p.y);
+            const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
+            const float tc = __ldg(tp + k);
+            if (d <= tc) {
+                if (d < tc || j <= __ldg(jcut_s + o + k)) {
+                    float w = 1.0f;
+                    if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
+                                            __ldg(wsum + (int64_t)slab * g.q + o + k));
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
+                    for (int r = 0; r < (RT ? RT : kMaxTref); ++r) {
+                        if (r < R) {
                             const float2 v = __ldg(dl_s + (o + k) * R + r);
-                            binr[r].x += w * v.x;
-                            binr[r].y += w * v.y;
+                            acc.binr[r].x += w * v.x;
+                            acc.binr[r].y += w * v.y;
                         }
-                        if (do_next) {
-                            const float2 v = __ldg(dn_s + o + k);
-                            nxt.x += v.x;
-                            nxt.y += v.y;
-                        }
+                    }
+                    if (do_next) {
+                        const float2 v = __ldg(dn_s + o + k);
+                        acc.nxt.x += v.x;
+                        acc.nxt.y += v.y;
                     }
                 }
             }
         }
     }
-    const int stride = R + (F2N ? 1 : 0);
-    float2 *out = part + ((int64_t)slab * g.n + j) * stride;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (!IWD) { binr[r].x *= invK; binr[r].y *= invK; }     // mean: one scale per bin
-        out[r] = binr[r];
+}
+
+// RT = compile-time R (1, 3, 5, 10) or 0 = runtime R; TH = cell rows per tile, NT = threads per CTA
+template <bool L1D, bool IWD, bool F2N, int RT, int TH, int NT>
+__global__ void __launch_bounds__(NT, TH == 8 ? (NT == 128 ? 8 : (NT == 160 ? 6 : 5)) : 3)
+lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, int refine, const int *__restrict__ cell_start,
+                         const float4 *__restrict__ sorted_all, const float *__restrict__ tau,
+                         const int *__restrict__ jcut, const float *__restrict__ wsum,
+                         const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
+                         const float *__restrict__ dlut, const float *__restrict__ df2n,
+                         float2 *__restrict__ part)
+{
+    __shared__ float2 s_key[kBwdWinCap];                    // (tau, jcut bits) of the staged LUT cells
+    __shared__ float2 s_dl[RT == 1 ? kBwdWinCap : 1];       // dLUT (single reference time)
+    __shared__ float2 s_dn[F2N ? kBwdWinCap : 1];           // d flow_to_next
+    __shared__ float s_rowmax[kBwdMaxRows], s_rowmax2[kBwdMaxRows];
+    constexpr int kBwdTileH = TH, kBwdBlock = NT;
+    __shared__ int s_run[kBwdTileH + 1], s_runbase[kBwdTileH];
+    __shared__ float s_tbest;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int bin = blockIdx.y, b = blockIdx.z;
+    const int slab = b * g.nb + bin;
+    const int R = RT ? RT : g.R;
+    const int ctx_n = (g.Wc + kBwdTileW - 1) / kBwdTileW;
+    const int cty = blockIdx.x / ctx_n, ctx = blockIdx.x - cty * ctx_n;
+    const int cy0 = cty * kBwdTileH, cy1 = min(cy0 + kBwdTileH - 1, g.Hc - 1);
+    const int cx0 = ctx * kBwdTileW, cx1 = min(cx0 + kBwdTileW - 1, g.Wc - 1);
+    const int *cstart = cell_start + (int64_t)slab * (g.NC + 1);
+    const float4 *sorted = sorted_all + (int64_t)slab * g.n;
+    const float fs = (float)g.s, inv_s = 1.0f / fs;
+    const int Wq = g.Wq;
+    // Pixel rectangle of the tile, widened a little (cells are assigned with a rounded product).
+    // The border cells of the grid also hold every point beyond it (cell_of clamps): tiles on the
+    // border extend outwards far enough to cover any point that can still be somebody's neighbour;
+    // the lattice ends at the grid, so the staged window does not grow with it.
+    constexpr float kFar = 1.0e6f;
+    const float Y0 = cy0 == 0 ? -kFar : (float)cy0 * g.cs - 0.01f;
+    const float Y1 = cy1 == g.Hc - 1 ? kFar : (float)(cy1 + 1) * g.cs + 0.01f;
+    const float X0 = cx0 == 0 ? -kFar : (float)cx0 * g.cs - 0.01f;
+    const float X1 = cx1 == g.Wc - 1 ? kFar : (float)(cx1 + 1) * g.cs + 0.01f;
+    // lattice index of a coordinate, clamped to the grid *in float* (kFar, huge reaches)
+    auto lat_lo = [&](float v, int hi) { return (int)fminf(fmaxf(floorf((v - g.off) * inv_s), 0.0f), (float)hi); };
+    auto lat_hi = [&](float v, int hi) { return (int)fminf(fmaxf(ceilf((v - g.off) * inv_s), 0.0f), (float)hi); };
+
+    if (tid <= kBwdTileH) {                                   // the tile's point runs, one per cell row
+        int acc = 0;
+        for (int r = 0; r < tid; ++r)
+            if (cy0 + r <= cy1)
+                acc += __ldg(cstart + (cy0 + r) * g.Wc + cx1 + 1) - __ldg(cstart + (cy0 + r) * g.Wc + cx0);
+        s_run[tid] = acc;
+        if (tid < kBwdTileH) s_runbase[tid] = cy0 + tid <= cy1 ? __ldg(cstart + (cy0 + tid) * g.Wc + cx0) : 0;
     }
-    if (F2N) out[R] = make_float2(nxt.x * invK, nxt.y * invK);
+    // reach of the tile: largest tau among the K-NN tiles (16x8 queries) closer to the rectangle
+    // than their own reach (same test as gather_generic, on the rectangle instead of the point)
+    if (tid >= 32 && tid < 64) {
+        const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
+        const int tiles_y = (g.Hq + kKnnTileH - 1) / kKnnTileH;
+        const float tm = __uint_as_float(__ldg(tau_max + slab));
+        float rho_g = L1D ? tm : approx_sqrt(tm);
+        rho_g = rho_g * 1.0001f + 1e-3f;
+        float tbest = -1.0f;
+        if (rho_g == rho_g) {
+            const int ty0 = lat_lo(Y0 - rho_g, g.Hq - 1) / kKnnTileH, ty1 = lat_hi(Y1 + rho_g, g.Hq - 1) / kKnnTileH;
+            const int tx0 = lat_lo(X0 - rho_g, Wq - 1) / kKnnTileW, tx1 = lat_hi(X1 + rho_g, Wq - 1) / kKnnTileW;
+            const unsigned *tmx = tile_max + (int64_t)slab * (tiles_x * tiles_y);
+            const int ntx = tx1 - tx0 + 1, ntt = ntx * (ty1 - ty0 + 1);
+            for (int t = lane; t < ntt; t += 32) {
+                const int ty = ty0 + t / ntx, tx = tx0 + t % ntx;
+                const float y_lo = (float)(ty * kKnnTileH * g.s) + g.off;
+                const float y_hi = (float)(min(ty * kKnnTileH + kKnnTileH - 1, g.Hq - 1) * g.s) + g.off;
+                const float x_lo = (float)(tx * kKnnTileW * g.s) + g.off;
+                const float x_hi = (float)(min(tx * kKnnTileW + kKnnTileW - 1, Wq - 1) * g.s) + g.off;
+                const float ddy = fmaxf(fmaxf(y_lo - Y1, Y0 - y_hi), 0.0f);
+                const float ddx = fmaxf(fmaxf(x_lo - X1, X0 - x_hi), 0.0f);
+                const float tmt = __uint_as_float(__ldg(tmx + ty * tiles_x + tx));
+                const float gap = L1D ? ddy + ddx : ddy * ddy + ddx * ddx;
+                if (gap <= tmt * 1.001f + 1e-2f) tbest = fmaxf(tbest, tmt);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tbest = fmaxf(tbest, __shfl_xor_sync(0xffffffffu, tbest, o));
+        if (lane == 0) s_tbest = tbest;
+    }
+    __syncthreads();
+    const int total = s_run[kBwdTileH];
+    if (total == 0) return;
+    const float tbest = s_tbest;
+    auto reach_of = [&](float t) { return t < 0.0f ? 0.0f : (L1D ? t : approx_sqrt(t)) * 1.0001f + 1e-3f; };
+    const float rho0 = reach_of(tbest);
+    // staged lattice window: every LUT cell within rho0 of the rectangle
+    const int iyA = lat_lo(Y0 - rho0, g.Hq - 1), iyB = lat_hi(Y1 + rho0, g.Hq - 1);
+    const int ixA = lat_lo(X0 - rho0, Wq - 1), ixB = lat_hi(X1 + rho0, Wq - 1);
+    const int nrows = iyB - iyA + 1, ncols = ixB - ixA + 1;
+    // rows are padded by three never-member entries so that the column loop runs in groups of four
+    const int ncp = ncols + 3;
+    const bool fast = tbest >= 0.0f && nrows >= 1 && ncols >= 1 && nrows <= kBwdMaxRows &&
+                      nrows * ncp <= kBwdWinCap;              // CTA-uniform
+    const float *tau_s = tau + (int64_t)slab * g.q;
+    const int *jcut_s = jcut + (int64_t)slab * g.q;
+    const float2 *dl_s = reinterpret_cast<const float2 *>(dlut) + (int64_t)slab * g.q * g.R;
+    const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
+                             : nullptr;
+    const bool do_next = F2N && bin < g.nb - 1;
+    float rho = rho0;
+    int jyA = iyA, jyB = iyB, jxA = ixA, jxB = ixB;          // refined window (inside the staged one)
+    if (fast) {
+        for (int lr = tid >> 5; lr < nrows; lr += kBwdBlock / 32) {     // one warp per lattice row
+            const int o = (iyA + lr) * Wq + ixA;
+            float rm = -1.0f;
+            for (int c = lane; c < ncp; c += 32) {
+                const bool real = c < ncols;
+                const float t = real ? __ldg(tau_s + o + c) : -1.0f;          // -1: d <= tau never holds
+                s_key[lr * ncp + c] = make_float2(t, real ? __int_as_float(__ldg(jcut_s + o + c)) : 0.0f);
+                if (RT == 1) s_dl[lr * ncp + c] = real ? __ldg(dl_s + o + c) : make_float2(0.f, 0.f);
+                if (F2N) s_dn[lr * ncp + c] = (real && do_next) ? __ldg(dn_s + o + c) : make_float2(0.f, 0.f);
+                rm = fmaxf(rm, t);
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o2));
+            if (lane == 0) s_rowmax[lr] = rm;
+        }
+        __syncthreads();
+        // The tile-level reach comes from whole 16x8-query tiles; the staged keys give a tighter
+        // one: the maximum over the window bounds the reach, which shrinks the window, whose row
+        // maxima (over its own columns only) bound every row of the walk.
+        float m1 = -1.0f;
+        if (!refine) m1 = tbest;
+        for (int lr = lane; lr < nrows; lr += 32) m1 = fmaxf(m1, s_rowmax[lr]);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o2));
+        const float rho1 = fminf(reach_of(m1), rho0);
+        jyA = max(iyA, lat_lo(Y0 - rho1, g.Hq - 1));
+        jyB = min(iyB, lat_hi(Y1 + rho1, g.Hq - 1));
+        jxA = max(ixA, lat_lo(X0 - rho1, Wq - 1));
+        jxB = min(ixB, lat_hi(X1 + rho1, Wq - 1));
+        for (int lr = (tid >> 5) + (jyA - iyA); lr <= jyB - iyA; lr += kBwdBlock / 32) {
+            float rm = -1.0f;
+            for (int c = jxA - ixA + lane; c <= jxB - ixA; c += 32) rm = fmaxf(rm, s_key[lr * ncp + c].x);
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o2));
+            // scaled once here: `rem` of the row walk is rowmax * 1.0001 + 1e-3 - dy2
+            if (lane == 0) s_rowmax2[lr] = rm < 0.0f ? -1.0f : rm * 1.0001f + 1e-3f;
+        }
+        __syncthreads();
+        float m2 = -1.0f;
+        for (int lr = jyA - iyA + lane; lr <= jyB - iyA; lr += 32) m2 = fmaxf(m2, s_rowmax2[lr]);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o2));
+        rho = fminf(reach_of(m2), rho1);
+    }
+
+    const float invK = 1.0f / (float)g.K;
+    const int stride = R + (F2N ? 1 : 0);
+    for (int t = tid; t < total; t += kBwdBlock) {
+        int row = 0;
+#pragma unroll
+        for (int r = 1; r < kBwdTileH; ++r) row += t >= s_run[r] ? 1 : 0;
+        const float4 rec = __ldg(sorted + s_runbase[row] + (t - s_run[row]));
+        const float2 p = make_float2(rec.x, rec.y);
+        const int j = __float_as_int(rec.z);
+        BwdAcc<L1D, IWD, F2N, RT> acc;
+        acc.clear();
+        const bool inside = p.x >= Y0 && p.x <= Y1 && p.y >= X0 && p.y <= X1;      // false for NaN
+        if (fast && inside) {
+            const float pyo = p.x - g.off, pxo = p.y - g.off;
+            const int iy0 = max(jyA, (int)fminf(fmaxf(floorf((pyo - rho) * inv_s), 0.0f), (float)g.Hq));
+            const int iy1 = min(jyB, (int)fminf(fmaxf(ceilf((pyo + rho) * inv_s), -1.0f), (float)g.Hq));
+            float qy = __fadd_rn((float)(iy0 * g.s), g.off);      // exact: multiples of 0.5
+            int rb = (iy0 - iyA) * ncp - ixA;                      // staged index of (iy, lattice column 0)
+            for (int iy = iy0; iy <= iy1; ++iy, qy += fs, rb += ncp) {
+                const float dy = __fsub_rn(qy, p.x);
+                const float dy2 = L1D ? fabsf(dy) : __fmul_rn(dy, dy);
+                // clip the row to the disc (l1: diamond) of the row's largest tau; conservative
+                const float rem = s_rowmax2[iy - iyA] - dy2;
+                if (!(rem >= 0.0f)) continue;
+                const float hx = (L1D ? rem : approx_sqrt(rem)) * 1.0001f + 1e-3f;
+                const int jx0 = max(jxA, (int)fminf(fmaxf(floorf((pxo - hx) * inv_s), 0.0f), (float)Wq));
+                const int jx1 = min(jxB, (int)fminf(fmaxf(ceilf((pxo + hx) * inv_s), -1.0f), (float)Wq));
+                const int nx = jx1 - jx0 + 1;
+                const int sb = rb + jx0;
+                const int o = iy * Wq + jx0;
+                float qx = __fadd_rn((float)(jx0 * g.s), g.off);   // exact: multiples of 0.5
+                const unsigned dl_base = (unsigned)__cvta_generic_to_shared(&s_dl[RT == 1 ? sb : 0]);
+#pragma unroll 1
+                for (int k4 = 0; k4 < nx; k4 += 4) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u, qx += fs) {       // columns past jx1: real cells or padding
+                    const int k = k4 + u;
+                    const float dx = __fsub_rn(qx, p.y);
+                    const float d = __fadd_rn(dy2, L1D ? fabsf(dx) : __fmul_rn(dx, dx));
+                    const float2 key = s_key[sb + k];
+                    if (RT == 1 && !IWD && !F2N) {
+                        // membership + predicated load + two predicated adds, branch free: about 60 %
+                        // of the candidates are members, a branch here would split every warp
+                        asm("{\n\t.reg .pred p, q;\n\t.reg .f32 vx, vy;\n\t"
+                            "setp.eq.f32 q, %2, %3;\n\t"
+                            "setp.le.and.s32 q, %4, %5, q;\n\t"
+                            "setp.lt.or.f32 p, %2, %3, q;\n\t"
+                            "@p ld.shared.v2.f32 {vx, vy}, [%6];\n\t"
+                            "@p add.rn.f32 %0, %0, vx;\n\t"
+                            "@p add.rn.f32 %1, %1, vy;\n\t}"
+                            : "+f"(acc.binr[0].x), "+f"(acc.binr[0].y)
+                            : "f"(d), "f"(key.x), "r"(j), "r"(__float_as_int(key.y)),
+                              "r"(dl_base + 8u * (unsigned)k));
+                        continue;
+                    }
+                    const bool member = d < key.x || (d == key.x && j <= __float_as_int(key.y));
+                    if (member) {
+                        float w = 1.0f;
+                        if (IWD) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(d, kIwdEps)),
+                                                __ldg(wsum + (int64_t)slab * g.q + o + k));
+#pragma unroll
+                        for (int r = 0; r < (RT ? RT : kMaxTref); ++r) {
+                            if (r < R) {
+                                const float2 v = RT == 1 ? s_dl[sb + k] : __ldg(dl_s + (o + k) * R + r);
+                                acc.binr[r].x += w * v.x;
+                                acc.binr[r].y += w * v.y;
+                            }
+                        }
+                    }
+                    if (F2N && member) {
+                        const float2 v = s_dn[sb + k];
+                        acc.nxt.x += v.x;
+                        acc.nxt.y += v.y;
+                    }
+                  }
+                }
+            }
+        } else {
+            BwdAcc<L1D, IWD, F2N, RT> slow;          // address-taken copy: keeps `acc` in registers
+            slow.clear();
+            const LatticeGeom lg{g.Hq, g.Wq, g.s, g.R, g.nb, g.q, g.off};
+            gather_generic<L1D, IWD, F2N, RT>(lg, slab, b, bin, j, p, tau, jcut, wsum, tau_max, tile_max, dlut,
+                                              df2n, slow);
+            acc = slow;
+        }
+        float2 *out = part + ((int64_t)slab * g.n + j) * stride;
+#pragma unroll
+        for (int r = 0; r < (RT ? RT : kMaxTref); ++r) {
+            if (r < R) {
+                if (!IWD) { acc.binr[r].x *= invK; acc.binr[r].y *= invK; }     // mean: one scale per bin
+                out[r] = acc.binr[r];
+            }
+        }
+        if (F2N) out[R] = make_float2(acc.nxt.x * invK, acc.nxt.y * invK);
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -1082,9 +1621,13 @@ static void launch_fast(const Geom &g, int bin, int chain_len, dim3 grid, cudaSt
     }
 }
 
-int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *ws,
+int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, char *ws,
                        float *flow_lut_out, int32_t *ind_out, float *dist_out, cudaStream_t st)
 {
+    static int fwd_opt = -1;                // experiment switch: bit 0 = no in-kernel second chance
+    if (fwd_opt < 0) { const char *e = getenv("CMAX_FWD_OPT"); fwd_opt = e ? atoi(e) : 0; }
+    Geom g = g_in;
+    g.dbg = fwd_opt;
     int *cell_start = reinterpret_cast<int *>(ws + L.cell_start);
     float4 *sorted = reinterpret_cast<float4 *>(ws + L.sorted);
     float2 *sflow = reinterpret_cast<float2 *>(ws + L.sflow);
@@ -1122,7 +1665,7 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     const int tiles = ((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
     StageScope sc(ST_KNN_SELECT, st);
     cudaMemsetAsync(tau_max, 0, sizeof(unsigned) * g.S, st);
-    cudaMemsetAsync(work_count, 0, sizeof(int), st);
+    cudaMemsetAsync(work_count, 0, sizeof(int) * 16, st);
     // the staged fast path needs the window to fit the static tables and S*q to fit an int
     const bool can_fast = g.r_fast <= 10 && g.S * (int64_t)g.q < (int64_t)INT32_MAX;
     float *lc = fused ? flow_lut_out : nullptr;
@@ -1151,10 +1694,21 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
                 else launch_fast<false, false>(g, bin, chain_len, grid, st, a);
             }
         }
-        knn_heap_kernel<<<148 * 16, kKnnBlock, smem_heap / 4, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
-                                                                  tau_max, tile_max, worklist, work_count,
-                                                                  fused ? 1 : 0, lut, lc, 8);
-        count_launch((per_bin ? chain_len : 1) + 1);
+        // work list: warp-cooperative select first, the per-thread heap for whatever that leaves
+        int *worklist2 = reinterpret_cast<int *>(ws + L.worklist2);
+        int *work_count2 = work_count + 8;
+        if (g.l1dist)
+            knn_warp_kernel<true><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, tau, jcut, tau_max,
+                                                               tile_max, worklist, work_count, fused ? 1 : 0, lut,
+                                                               lc, worklist2, work_count2);
+        else
+            knn_warp_kernel<false><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, tau, jcut, tau_max,
+                                                                tile_max, worklist, work_count, fused ? 1 : 0, lut,
+                                                                lc, worklist2, work_count2);
+        knn_heap_kernel<<<148 * 4, kKnnBlock, smem_heap / 4, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
+                                                                 tau_max, tile_max, worklist2, work_count2,
+                                                                 fused ? 1 : 0, lut, lc, 8);
+        count_launch((per_bin ? chain_len : 1) + 2);
     } else {
         cudaMemsetAsync(tile_max, 0, sizeof(unsigned) * g.S * tiles, st);
         knn_heap_kernel<<<148 * 8, kKnnBlock, smem_heap, st>>>(traj, g, -1, cell_start, sorted, tau, jcut,
@@ -1197,12 +1751,41 @@ int launch_lut_forward(const Geom &g, const Layout &L, const float *traj, char *
     return check_launch();
 }
 
+struct BwdArgs {
+    const float *traj;
+    const int *cell_start;
+    const float4 *sorted;
+    const float *tau;
+    const int *jcut;
+    const float *wsum;
+    const unsigned *tmax, *tile_max;
+    const float *dlut, *df2n;
+    float2 *part;
+    int big_tile, refine, nthr;
+};
+
 template <bool L1D, bool IWD, bool F2N>
-static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *traj, const float *tau,
-                       const int *jcut, const float *wsum, const unsigned *tmax,
-                       const unsigned *tile_max, const float *dlut, const float *df2n, float2 *part)
+static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const BwdArgs &a)
 {
-#define BWD_LAUNCH(RT_) lut_backward_kernel<L1D, IWD, F2N, RT_><<<grid, 64, 0, st>>>(traj, g, tau, jcut, wsum, tmax, tile_max, dlut, df2n, part)
+#define BWD_LAUNCH(RT_)                                                                                         \
+    do {                                                                                                         \
+        if (a.big_tile)                                                                                          \
+            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 16, 288><<<grid, 288, 0, st>>>(                      \
+                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
+                a.df2n, a.part);                                                                                 \
+        else if (a.nthr == 192)                                                                                  \
+            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 192><<<grid, 192, 0, st>>>(                       \
+                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
+                a.df2n, a.part);                                                                                 \
+        else if (a.nthr == 160)                                                                                  \
+            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 160><<<grid, 160, 0, st>>>(                       \
+                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
+                a.df2n, a.part);                                                                                 \
+        else                                                                                                     \
+            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 128><<<grid, 128, 0, st>>>(                       \
+                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
+                a.df2n, a.part);                                                                                 \
+    } while (0)
     if (g.R == 1) BWD_LAUNCH(1);
     else if (!F2N && g.R == 3) BWD_LAUNCH(F2N ? 0 : 3);        // compile-time R keeps the per-reference
     else if (!F2N && g.R == 5) BWD_LAUNCH(F2N ? 0 : 5);        // accumulators in registers (on_flow_to_next
@@ -1214,28 +1797,40 @@ static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const float *t
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
                         float *dtraj, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.n + 63) / 64), (unsigned)g.nb, (unsigned)g.B);
+    static int opt = -1;                    // experiment switch: bit 0 = 16x16-cell tiles, bit 1 = no refinement
+    if (opt < 0) { const char *e = getenv("CMAX_BWD_OPT"); opt = e ? atoi(e) : 0; }
+    const int th = (opt & 1) ? 16 : 8;
+    const unsigned ctiles = (unsigned)(((g.Hc + th - 1) / th) * ((g.Wc + kBwdTileW - 1) / kBwdTileW));
+    dim3 grid(ctiles, (unsigned)g.nb, (unsigned)g.B);
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
     float2 *dtraj_part = reinterpret_cast<float2 *>(ws + L.bpart);
-    const float *tau = reinterpret_cast<const float *>(ws + L.tau);
-    const int *jcut = reinterpret_cast<const int *>(ws + L.jcut);
-    const float *wsum = reinterpret_cast<const float *>(ws + L.wsum);
-    const unsigned *tmax = reinterpret_cast<const unsigned *>(ws + L.tau_max);
-    const unsigned *tile_max = reinterpret_cast<const unsigned *>(ws + L.tile_max);
+    BwdArgs a;
+    a.traj = traj;
+    a.cell_start = reinterpret_cast<const int *>(ws + L.cell_start);
+    a.sorted = reinterpret_cast<const float4 *>(ws + L.sorted);
+    a.tau = reinterpret_cast<const float *>(ws + L.tau);
+    a.jcut = reinterpret_cast<const int *>(ws + L.jcut);
+    a.wsum = reinterpret_cast<const float *>(ws + L.wsum);
+    a.tmax = reinterpret_cast<const unsigned *>(ws + L.tau_max);
+    a.tile_max = reinterpret_cast<const unsigned *>(ws + L.tile_max);
+    a.dlut = reinterpret_cast<const float *>(ws + L.dlut);
+    a.df2n = reinterpret_cast<const float *>(ws + L.df2n);
+    a.part = dtraj_part;
+    a.big_tile = opt & 1;
+    a.refine = (opt & 2) ? 0 : 1;
+    a.nthr = (opt & 4) ? 192 : ((opt & 8) ? 160 : 128);
     StageScope sc(ST_LUT_BWD, st);
     count_launch(2);
-    const float *dlut = reinterpret_cast<const float *>(ws + L.dlut);
-    const float *df2n = reinterpret_cast<const float *>(ws + L.df2n);
     const int key = (g.l1dist ? 4 : 0) | (g.iwd ? 2 : 0) | (want_next ? 1 : 0);
     switch (key) {
-    case 0: launch_bwd<false, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 1: launch_bwd<false, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 2: launch_bwd<false, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 3: launch_bwd<false, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 4: launch_bwd<true, false, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 5: launch_bwd<true, false, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    case 6: launch_bwd<true, true, false>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
-    default: launch_bwd<true, true, true>(g, grid, st, traj, tau, jcut, wsum, tmax, tile_max, dlut, df2n, dtraj_part); break;
+    case 0: launch_bwd<false, false, false>(g, grid, st, a); break;
+    case 1: launch_bwd<false, false, true>(g, grid, st, a); break;
+    case 2: launch_bwd<false, true, false>(g, grid, st, a); break;
+    case 3: launch_bwd<false, true, true>(g, grid, st, a); break;
+    case 4: launch_bwd<true, false, false>(g, grid, st, a); break;
+    case 5: launch_bwd<true, false, true>(g, grid, st, a); break;
+    case 6: launch_bwd<true, true, false>(g, grid, st, a); break;
+    default: launch_bwd<true, true, true>(g, grid, st, a); break;
     }
     dim3 grid2((unsigned)((g.n + 127) / 128), (unsigned)g.B);
     lut_backward_assemble_kernel<<<grid2, 128, 0, st>>>(g, dtraj_part, want_next ? 1 : 0, dtraj);

@@ -82,21 +82,34 @@ class _TrajectoriesFunction(torch.autograd.Function):
                                            int(xy_order), int(add_offsets), cabi.ptr(out),
                                            cabi.stream_ptr(cg.device))
         cabi.check(rc, "cmax_trajectories_forward")
-        ctx.save_for_backward(phi)
+        # a learned basis (basis.py:26-27: phi = MLP(t)) needs d loss / d phi, which contracts the
+        # trajectory gradient with the tile-centre coefficients: keep those (tiny) when asked for
+        tile_coeff = None
+        if phi.requires_grad:
+            tile_coeff = cg[:, :, :, o::patch, o::patch].sum(1).reshape(B, 2 * K, ny * nx)
+        ctx.save_for_backward(phi.detach(), tile_coeff)
         ctx.meta = (B, S, K, H, W, patch, n_t, int(xy_order))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = cabi.load()
-        (phi,) = ctx.saved_tensors
+        phi, tile_coeff = ctx.saved_tensors
         B, S, K, H, W, patch, n_t, xy = ctx.meta
         g = grad_out.detach().to(torch.float32).contiguous()
-        dcg = torch.empty((B, S, 2 * K, H, W), dtype=torch.float32, device=g.device)
-        rc = lib.cmax_trajectories_backward(cabi.ptr(g), cabi.ptr(phi), B, S, K, H, W, patch, n_t,
-                                            xy, cabi.ptr(dcg), cabi.stream_ptr(g.device))
-        cabi.check(rc, "cmax_trajectories_backward")
-        return dcg, None, None, None, None
+        dcg = None
+        if ctx.needs_input_grad[0]:
+            dcg = torch.empty((B, S, 2 * K, H, W), dtype=torch.float32, device=g.device)
+            rc = lib.cmax_trajectories_backward(cabi.ptr(g), cabi.ptr(phi), B, S, K, H, W, patch, n_t,
+                                                xy, cabi.ptr(dcg), cabi.stream_ptr(g.device))
+            cabi.check(rc, "cmax_trajectories_backward")
+        dphi = None
+        if ctx.needs_input_grad[1] and tile_coeff is not None:
+            # traj[b,t,j,a] = sum_k phi[t,k] c_a[b,k,j]  =>  dphi[t,k] = sum_{b,j,a} dtraj[b,t,j,a] c_a[b,k,j]
+            first, second = tile_coeff[:, :K], tile_coeff[:, K:]
+            cy, cx = (second, first) if xy else (first, second)
+            dphi = torch.einsum("btj,bkj->tk", g[..., 0], cy) + torch.einsum("btj,bkj->tk", g[..., 1], cx)
+        return dcg, dphi, None, None, None
 
 
 def calculate_trajectories_at_t(coeff_grid: torch.Tensor, times: torch.Tensor, patch_size: int,
@@ -120,8 +133,12 @@ def calculate_trajectories_at_t(coeff_grid: torch.Tensor, times: torch.Tensor, p
 
 def trajectories_from_table(coeff_grid: torch.Tensor, phi: torch.Tensor, patch_size: int,
                             add_offsets: bool = True, xy_order: bool = False) -> torch.Tensor:
-    """Same as above with a caller-built basis table ``phi [n_t, K]`` (already anchor-subtracted)."""
+    """Same as above with a caller-built basis table ``phi [n_t, K]`` (already anchor-subtracted),
+    e.g. the learned MLP basis of basis.py:26-27.  Differentiable in ``coeff_grid`` *and* ``phi``
+    (the reference back-propagates into ``basis_network(times)``)."""
     if coeff_grid.dim() == 4:
         coeff_grid = coeff_grid[:, None]
-    return _TrajectoriesFunction.apply(coeff_grid, phi.detach().to(torch.float32).contiguous(),
+    if not coeff_grid.is_cuda:
+        raise RuntimeError("trajectories_from_table (B200) needs CUDA tensors; no CPU path")
+    return _TrajectoriesFunction.apply(coeff_grid, phi.to(torch.float32).contiguous(),
                                        int(patch_size), bool(xy_order), bool(add_offsets))
