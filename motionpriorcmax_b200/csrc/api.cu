@@ -141,7 +141,8 @@ static void take_knn(const Geom &g, Layout &L, Take &take)
     const size_t tiles = (size_t)((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
     L.cell_start = take(sizeof(int) * g.S * (g.NC + 1));
     L.sorted = take(sizeof(float4) * g.S * g.n);
-    L.sflow = take(g.R == 1 ? sizeof(float2) * g.S * g.n : 16);
+    L.recs = take(sizeof(float4) * g.S * g.n);
+    L.sorted_j = take(sizeof(int) * g.S * g.n);
     L.tau = take(sizeof(float) * g.S * g.q);
     L.jcut = take(sizeof(int) * g.S * g.q);
     L.wsum = take(g.iwd ? sizeof(float) * g.S * g.q : 16);

@@ -53,7 +53,7 @@ struct Header {               // first 1 KiB of the workspace
 };
 
 struct Layout {
-    size_t header, focus_partials, plane_stats, smooth_partials, cell_start, sorted, sflow, tau, jcut, wsum,
+    size_t header, focus_partials, plane_stats, smooth_partials, cell_start, sorted, recs, sorted_j, tau, jcut, wsum,
         tau_max, tile_max, worklist, worklist2, work_count, bpart, lut, f2n, raw, raw_i64, dimg, dlut, dlut_i64, df2n, total;
     int n_img_blocks, n_sm_blocks;
 };

@@ -49,10 +49,12 @@ __device__ __forceinline__ const float2 *slab_points(const float *traj, const Ge
 }
 
 __global__ void __launch_bounds__(1024)
-bin_points_kernel(const float *__restrict__ traj, Geom g, int *__restrict__ cell_start,
-                  float4 *__restrict__ sorted, float2 *__restrict__ sflow)
+bin_points_kernel(const float *__restrict__ traj, Geom g, int fused, int *__restrict__ cell_start,
+                  float4 *__restrict__ sorted, float4 *__restrict__ recs, int *__restrict__ sorted_j)
 {
-    // record = (y, x, trajectory index, unused); sflow = traj(t_ref) - traj(t_mid) when R == 1
+    // sorted = (y, x, trajectory index, unused): what the generic kernels walk;
+    // recs   = (y, x, flow_y, flow_x), flow = traj(t_ref) - traj(t_mid) when R == 1 (else 0), and
+    // sorted_j = the index alone: the 16-byte records the staged K-NN kernel pulls in with bulk copies
     extern __shared__ int cnt[];                 // [NC] counters, then cursors
     __shared__ int warp_tot[32];
     const int64_t slab = blockIdx.x;
@@ -127,15 +129,22 @@ bin_points_kernel(const float *__restrict__ traj, Geom g, int *__restrict__ cell
             }
         }
     }
-    if (sflow != nullptr) {                       // R == 1: flow to the reference time, sorted order
-        __syncthreads();
+    __syncthreads();
+    {
         const int64_t b = slab / g.nb;
         const float2 *tref = reinterpret_cast<const float2 *>(traj) + (b * (g.R + g.nb)) * g.n;
-        float2 *fo = sflow + slab * g.n;
+        float4 *ro = recs + slab * g.n;
+        int *jo = sorted_j + slab * g.n;
         for (int64_t i = tid; i < g.n; i += nt) {
             const float4 r = out[i];
-            const float2 pr = __ldg(tref + __float_as_int(r.z));
-            fo[i] = make_float2(__fsub_rn(pr.x, r.x), __fsub_rn(pr.y, r.y));     // focus.py:141
+            const int j = __float_as_int(r.z);
+            float2 f = make_float2(0.0f, 0.0f);
+            if (fused) {                              // R == 1: flow to the reference time (focus.py:141)
+                const float2 pr = __ldg(tref + j);
+                f = make_float2(__fsub_rn(pr.x, r.x), __fsub_rn(pr.y, r.y));
+            }
+            ro[i] = make_float4(r.x, r.y, f.x, f.y);
+            jo[i] = j;
         }
     }
 }
@@ -282,12 +291,35 @@ __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
 }
 
 // staged record: (y, x) and, when the LUT entry is fused into the selection, the flow to t_ref
-template <bool FUSED> struct StageRec { typedef float2 T; };
-template <> struct StageRec<true> { typedef float4 T; };
 __device__ __forceinline__ float2 rec_flow(const float4 &r) { return make_float2(r.z, r.w); }
-__device__ __forceinline__ float2 rec_flow(const float2 &) { return make_float2(0.f, 0.f); }
-__device__ __forceinline__ float4 make_rec(float y, float x, float2 f, float4 *) { return make_float4(y, x, f.x, f.y); }
-__device__ __forceinline__ float2 make_rec(float y, float x, float2, float2 *) { return make_float2(y, x); }
+
+// ---- bulk async copies (TMA engine, no tensor map): global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(parity)
+                 : "memory");
+}
 
 // One candidate of the single-pass bracket scan, branch free (a branch per outcome splits every
 // warp: the three outcomes are about 55 % / 20 % / 25 % of the candidates):
@@ -330,15 +362,16 @@ __device__ __forceinline__ void classify(float d, float lo, float hi, float2 f, 
 template <bool L1D, bool FUSED, bool GUESS>
 __global__ void __launch_bounds__(kKnnBlock, 8)
 knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_start,
-                const float4 *__restrict__ sorted_all, const float2 *__restrict__ sflow_all,
+                const float4 *__restrict__ recs_all, const int *__restrict__ sorted_j_all,
                 float *__restrict__ lut, float *__restrict__ lut_copy, float *__restrict__ tau,
                 int *__restrict__ jcut, unsigned *__restrict__ tau_max,
                 unsigned *__restrict__ tile_max, int *__restrict__ worklist,
                 int *__restrict__ work_count)
 {
-    typedef typename StageRec<FUSED>::T Rec;
-    __shared__ Rec s_pt[kStageCap];
+    typedef float4 Rec;                                 // (y, x, flow_y, flow_x)
+    __shared__ __align__(16) Rec s_pt[kStageCap];
     __shared__ int s_pj[kStageCap];
+    __shared__ __align__(8) unsigned long long s_bar;   // completion of the bulk copies
     __shared__ unsigned short s_cell[kWinRows][kWinCols + 1];     // local run starts (< kStageCap)
     // boundary candidates: only the staged index is kept (u16, + the slice id in bits 10..13);
     // distances are recomputed from the staged point on demand
@@ -361,7 +394,8 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
     const int iy = ty * kKnnTileH + tid / kKnnTileW, ix = tx * kKnnTileW + tid % kKnnTileW;
     const bool active = iy < g.Hq && ix < g.Wq;
     const int *cstart = cell_start + (int64_t)slab * (g.NC + 1);
-    const float4 *sorted = sorted_all + (int64_t)slab * g.n;
+    const float4 *recs = recs_all + (int64_t)slab * g.n;
+    const int *sorted_j = sorted_j_all + (int64_t)slab * g.n;
 
     // ---- the tile's cell window -----------------------------------------------------------
     // radius r_fast in the interior; tiles whose window the grid border clips get a larger radius
@@ -387,7 +421,10 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
     const int wx0 = max(cx_lo - r, 0), wx1 = min(cx_hi + r, g.Wc - 1);
     const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 1;
 
-    if (tid == 0) blk_max = 0u;
+    if (tid == 0) {
+        blk_max = 0u;
+        mbar_init(&s_bar, 1);
+    }
     if (tid < 32) {                                   // row run lengths -> exclusive scan
         int len = 0;
         if (tid < nrow)
@@ -404,27 +441,33 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
     __syncthreads();
     const int total = s_rowbase[nrow];
     const bool staged = total <= kStageCap;           // CTA-uniform
-    if (staged) {                                      // one warp per window row
+    if (staged) {
+        // The records of a window row are one contiguous run of 16-byte records in HBM: one bulk
+        // async copy per row (issued by the lanes of warp 0, completion counted on the mbarrier)
+        // instead of a load / store pair per record and thread.
+        if (tid < 32) {
+            if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(total - kRowPad * nrow) * 16u);
+            __syncwarp();
+            if (tid < nrow) {
+                const int ga = __ldg(cstart + (wy0 + tid) * g.Wc + wx0);
+                const int base = s_rowbase[tid], len = s_rowbase[tid + 1] - base - kRowPad;
+                if (len > 0) bulk_g2s(&s_pt[base], recs + ga, (unsigned)len * 16u, &s_bar);
+            }
+        }
         const int lane = tid & 31;
-        const float2 *sfl = FUSED ? sflow_all + (int64_t)slab * g.n : nullptr;
-        for (int lr = tid >> 5; lr < nrow; lr += kKnnBlock / 32) {
+        for (int lr = tid >> 5; lr < nrow; lr += kKnnBlock / 32) {       // one warp per window row
             const int *crow = cstart + (wy0 + lr) * g.Wc + wx0;
             const int ga = __ldg(crow);
             const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base - kRowPad;
             for (int lc = lane; lc <= ncol; lc += 32)
                 s_cell[lr][lc] = (unsigned short)min(__ldg(crow + lc) - ga + base, kStageCap);
-            for (int k = lane; k < len + kRowPad; k += 32) {
-                if (k < len) {
-                    const float4 rec = __ldg(sorted + ga + k);
-                    s_pt[base + k] = make_rec(rec.x, rec.y, FUSED ? __ldg(sfl + ga + k) : make_float2(0.f, 0.f),
-                                              (Rec *)nullptr);
-                    s_pj[base + k] = __float_as_int(rec.z);
-                } else {                                   // sentinel: infinitely far, never listed
-                    s_pt[base + k] = make_rec(1e30f, 1e30f, make_float2(0.f, 0.f), (Rec *)nullptr);
-                    s_pj[base + k] = 0x7fffffff;
-                }
+            for (int k = lane; k < len; k += 32) s_pj[base + k] = __ldg(sorted_j + ga + k);
+            if (lane < kRowPad) {                          // sentinels: infinitely far, never listed
+                s_pt[base + len + lane] = make_float4(1e30f, 1e30f, 0.0f, 0.0f);
+                s_pj[base + len + lane] = 0x7fffffff;
             }
         }
+        mbar_wait(&s_bar, 0);
     }
     __syncthreads();
 
@@ -841,7 +884,7 @@ knn_heap_kernel(const float *__restrict__ traj, Geom g, int bin, const int *__re
 template <bool L1D>
 __global__ void __launch_bounds__(kKnnBlock)
 knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted_all,
-                const float2 *__restrict__ sflow_all, float *__restrict__ tau, int *__restrict__ jcut,
+                const float4 *__restrict__ recs_all, float *__restrict__ tau, int *__restrict__ jcut,
                 unsigned *__restrict__ tau_max, unsigned *__restrict__ tile_max,
                 const int *__restrict__ worklist, const int *__restrict__ work_count, int fused,
                 float *__restrict__ lut, float *__restrict__ lut_copy, int *__restrict__ worklist2,
@@ -861,7 +904,7 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
         const Query q = make_query((int)(sq - slab * g.q), g);
         const int *cstart = cell_start + slab * (g.NC + 1);
         const float4 *sorted = sorted_all + slab * g.n;
-        const float2 *sfl = fused ? sflow_all + slab * g.n : nullptr;
+        const float4 *sfl = recs_all + slab * g.n;                 // (y, x, flow_y, flow_x)
         const float t0 = tau[sq];
         float est = t0 < 0.0f ? -t0 : (L1D ? sqrtf(tau_nom * 1.5707963f) : tau_nom);
         float lo = 0.45f * est, hi = 1.7f * est;
@@ -934,9 +977,9 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
                         j = __float_as_int(rec.z);
                         bk = bucket_of(d, lo, invw);
                         if (fused && bk < bstar) {
-                            const float2 f = __ldg(sfl + i);
-                            ay = __fadd_rn(ay, f.x);
-                            ax = __fadd_rn(ax, f.y);
+                            const float4 f = __ldg(sfl + i);
+                            ay = __fadd_rn(ay, f.z);
+                            ax = __fadd_rn(ax, f.w);
                         }
                     }
                     const unsigned hit = __ballot_sync(0xffffffffu, bk == bstar);
@@ -962,9 +1005,9 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
                 rank += lex_less(du, ju, md, mj) ? 1 : 0;
             }
             if (fused && have && rank < need) {
-                const float2 f = __ldg(sfl + s_i[wid][lane]);
-                ay = __fadd_rn(ay, f.x);
-                ax = __fadd_rn(ax, f.y);
+                const float4 f = __ldg(sfl + s_i[wid][lane]);
+                ay = __fadd_rn(ay, f.z);
+                ax = __fadd_rn(ax, f.w);
             }
             const unsigned kth = __ballot_sync(0xffffffffu, have && rank == need - 1);
             const int src = __ffs(kth) - 1;
@@ -1590,7 +1633,8 @@ const int *g_last_work_count = nullptr;     // inspection hook (cmax_last_workli
 struct FastArgs {
     const int *cell_start;
     const float4 *sorted;
-    const float2 *sflow;
+    const float4 *recs;
+    const int *sorted_j;
     float *lut, *lut_copy, *tau;
     int *jcut;
     unsigned *tau_max, *tile_max;
@@ -1602,7 +1646,7 @@ static void launch_fast(const Geom &g, int bin, int chain_len, dim3 grid, cudaSt
 {
     if (bin <= 0)
         knn_fast_kernel<L1D, FUSED, false><<<grid, kKnnBlock, 0, st>>>(
-            g, bin, chain_len, a.cell_start, a.sorted, a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
+            g, bin, chain_len, a.cell_start, a.recs, a.sorted_j, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max,
             a.tile_max, a.worklist, a.work_count);
     else {
         cudaLaunchConfig_t cfg = {};
@@ -1615,8 +1659,8 @@ static void launch_fast(const Geom &g, int bin, int chain_len, dim3 grid, cudaSt
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, knn_fast_kernel<L1D, FUSED, true>, g, bin, chain_len, a.cell_start, a.sorted,
-                           a.sflow, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max, a.tile_max, a.worklist,
+        cudaLaunchKernelEx(&cfg, knn_fast_kernel<L1D, FUSED, true>, g, bin, chain_len, a.cell_start, a.recs,
+                           a.sorted_j, a.lut, a.lut_copy, a.tau, a.jcut, a.tau_max, a.tile_max, a.worklist,
                            a.work_count);
     }
 }
@@ -1630,7 +1674,8 @@ int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, cha
     g.dbg = fwd_opt;
     int *cell_start = reinterpret_cast<int *>(ws + L.cell_start);
     float4 *sorted = reinterpret_cast<float4 *>(ws + L.sorted);
-    float2 *sflow = reinterpret_cast<float2 *>(ws + L.sflow);
+    float4 *recs = reinterpret_cast<float4 *>(ws + L.recs);
+    int *sorted_j = reinterpret_cast<int *>(ws + L.sorted_j);
     float *tau = reinterpret_cast<float *>(ws + L.tau);
     int *jcut = reinterpret_cast<int *>(ws + L.jcut);
     unsigned *tau_max = reinterpret_cast<unsigned *>(ws + L.tau_max);
@@ -1658,8 +1703,8 @@ int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, cha
     const bool fused = !test_entry && g.R == 1 && !g.iwd;
     {
         StageScope sc(ST_BIN_POINTS, st);
-        bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, cell_start, sorted,
-                                                                 fused ? sflow : nullptr);
+        bin_points_kernel<<<(unsigned)g.S, 1024, smem_bin, st>>>(traj, g, fused ? 1 : 0, cell_start, sorted, recs,
+                                                                 sorted_j);
         count_launch();
     }
     const int tiles = ((g.Wq + kKnnTileW - 1) / kKnnTileW) * ((g.Hq + kKnnTileH - 1) / kKnnTileH);
@@ -1670,7 +1715,7 @@ int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, cha
     const bool can_fast = g.r_fast <= 10 && g.S * (int64_t)g.q < (int64_t)INT32_MAX;
     float *lc = fused ? flow_lut_out : nullptr;
     if (can_fast) {
-        const FastArgs a{cell_start, sorted, sflow, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count};
+        const FastArgs a{cell_start, sorted, recs, sorted_j, lut, lc, tau, jcut, tau_max, tile_max, worklist, work_count};
         // Few samples: per-bin launches (previous-bin bracket) would serialise 15 tiny grids, so
         // run the self-contained two-pass kernel on every slab at once instead.
         // (the inspection entry always chains, so the bracket path is testable at any batch size)
@@ -1698,11 +1743,11 @@ int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, cha
         int *worklist2 = reinterpret_cast<int *>(ws + L.worklist2);
         int *work_count2 = work_count + 8;
         if (g.l1dist)
-            knn_warp_kernel<true><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, tau, jcut, tau_max,
+            knn_warp_kernel<true><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, recs, tau, jcut, tau_max,
                                                                tile_max, worklist, work_count, fused ? 1 : 0, lut,
                                                                lc, worklist2, work_count2);
         else
-            knn_warp_kernel<false><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, sflow, tau, jcut, tau_max,
+            knn_warp_kernel<false><<<148 * 8, kKnnBlock, 0, st>>>(g, cell_start, sorted, recs, tau, jcut, tau_max,
                                                                 tile_max, worklist, work_count, fused ? 1 : 0, lut,
                                                                 lc, worklist2, work_count2);
         knn_heap_kernel<<<148 * 4, kKnnBlock, smem_heap / 4, st>>>(traj, g, 0, cell_start, sorted, tau, jcut,
