@@ -890,8 +890,10 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
                 float *__restrict__ lut, float *__restrict__ lut_copy, int *__restrict__ worklist2,
                 int *__restrict__ work_count2)
 {
+    constexpr int kWarpRows = 96;                       // rows of cells one query's extent may span
     __shared__ float s_d[kKnnBlock / 32][32];
     __shared__ int s_j[kKnnBlock / 32][32], s_i[kKnnBlock / 32][32];
+    __shared__ int s_ra[kKnnBlock / 32][kWarpRows], s_rp[kKnnBlock / 32][kWarpRows];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int total = work_count[0];
     const int tiles_x = (g.Wq + kKnnTileW - 1) / kKnnTileW;
@@ -918,19 +920,50 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
             const int c0 = (int)fminf(fmaxf(floorf((q.qx - sqr) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
             const int c1 = (int)fminf(fmaxf(floorf((q.qx + sqr) * g.inv_cs), 0.0f), (float)(g.Wc - 1));
             const bool whole = r0 == 0 && c0 == 0 && r1 == g.Hc - 1 && c1 == g.Wc - 1;
+            // row runs of the extent, flattened: the lanes fetch the run bounds of all rows at once
+            // and every candidate index becomes an independent load (a row-by-row walk is one long
+            // chain of dependent global loads: ~50 us for the whole kernel)
+            const int nrows = r1 - r0 + 1;
+            if (nrows > kWarpRows) break;
+            int T = 0;
+            for (int rb = 0; rb < nrows; rb += 32) {
+                const int rr = rb + lane;
+                int a = 0, len = 0;
+                if (rr < nrows) {
+                    a = __ldg(cstart + (r0 + rr) * g.Wc + c0);
+                    len = __ldg(cstart + (r0 + rr) * g.Wc + c1 + 1) - a;
+                }
+                int incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (rr < nrows) {
+                    s_ra[wid][rr] = a - (T + incl - len);       // candidate f of this row sits at s_ra + f
+                    s_rp[wid][rr] = T + incl - len;             // first flat index of the row
+                }
+                T += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+            auto flat_to_index = [&](int f) {                   // last row whose first flat index is <= f
+                int lo_r = 0, hi_r = nrows - 1;
+                while (lo_r < hi_r) {
+                    const int mid = (lo_r + hi_r + 1) >> 1;
+                    if (s_rp[wid][mid] <= f) lo_r = mid; else hi_r = mid - 1;
+                }
+                return s_ra[wid][lo_r] + f;
+            };
             // ---- pass 1 ------------------------------------------------------------------------
             unsigned hlo = 0u, hhi = 0u;              // 8 counters x 8 bit per lane
             int mine = 0;
-            for (int row = r0; row <= r1; ++row) {
-                const int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
-                for (int i = a + lane; i < e; i += 32) {
-                    const float4 rec = __ldg(sorted + i);
-                    const int bk = bucket_of(knn_dist(q.qy, q.qx, rec.x, rec.y, L1D), lo, invw);
-                    const unsigned inc = 1u << ((bk & 3) << 3);
-                    hlo += bk < 4 ? inc : 0u;
-                    hhi += (bk >= 4 && bk < 8) ? inc : 0u;
-                    ++mine;
-                }
+            for (int f = lane; f < T; f += 32) {
+                const float4 rec = __ldg(sorted + flat_to_index(f));
+                const int bk = bucket_of(knn_dist(q.qy, q.qx, rec.x, rec.y, L1D), lo, invw);
+                const unsigned inc = 1u << ((bk & 3) << 3);
+                hlo += bk < 4 ? inc : 0u;
+                hhi += (bk >= 4 && bk < 8) ? inc : 0u;
+                ++mine;
             }
             if (__any_sync(0xffffffffu, mine > 255)) break;       // packed counters could have wrapped
             int bstar = -1, below = 0, in_b = 0, cum = 0;
@@ -964,33 +997,30 @@ knn_warp_kernel(Geom g, const int *__restrict__ cell_start, const float4 *__rest
             // ---- pass 2: sure members and the slice ---------------------------------------------
             float ay = 0.0f, ax = 0.0f;
             int base = 0;
-            for (int row = r0; row <= r1; ++row) {
-                const int a = __ldg(cstart + row * g.Wc + c0), e = __ldg(cstart + row * g.Wc + c1 + 1);
-                for (int i0 = a; i0 < e; i0 += 32) {       // warp-uniform trip count (ballots inside)
-                    const int i = i0 + lane;
-                    int bk = 8;
-                    float d = 0.0f;
-                    int j = 0;
-                    if (i < e) {
-                        const float4 rec = __ldg(sorted + i);
-                        d = knn_dist(q.qy, q.qx, rec.x, rec.y, L1D);
-                        j = __float_as_int(rec.z);
-                        bk = bucket_of(d, lo, invw);
-                        if (fused && bk < bstar) {
-                            const float4 f = __ldg(sfl + i);
-                            ay = __fadd_rn(ay, f.z);
-                            ax = __fadd_rn(ax, f.w);
-                        }
+            for (int f0 = 0; f0 < T; f0 += 32) {           // warp-uniform trip count (ballots inside)
+                const int f = f0 + lane;
+                int bk = 8, i = 0, j = 0;
+                float d = 0.0f;
+                if (f < T) {
+                    i = flat_to_index(f);
+                    const float4 rec = __ldg(sorted + i);
+                    d = knn_dist(q.qy, q.qx, rec.x, rec.y, L1D);
+                    j = __float_as_int(rec.z);
+                    bk = bucket_of(d, lo, invw);
+                    if (fused && bk < bstar) {
+                        const float4 fl = __ldg(sfl + i);
+                        ay = __fadd_rn(ay, fl.z);
+                        ax = __fadd_rn(ax, fl.w);
                     }
-                    const unsigned hit = __ballot_sync(0xffffffffu, bk == bstar);
-                    if (bk == bstar) {
-                        const int pos = base + __popc(hit & lt_mask);
-                        s_d[wid][pos] = d;
-                        s_j[wid][pos] = j;
-                        s_i[wid][pos] = i;
-                    }
-                    base += __popc(hit);
                 }
+                const unsigned hit = __ballot_sync(0xffffffffu, bk == bstar);
+                if (bk == bstar) {
+                    const int pos = base + __popc(hit & lt_mask);
+                    s_d[wid][pos] = d;
+                    s_j[wid][pos] = j;
+                    s_i[wid][pos] = i;
+                }
+                base += __popc(hit);
             }
             __syncwarp();
             // rank the slice by (distance, index): lane l owns candidate l

@@ -33,3 +33,8 @@ def max_rel(a, b):
     b = np.asarray(b, np.float64)
     den = np.abs(b).max()
     return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+# (mode, rel. error, sign-flipped pixels, largest flipped |response| / mean |response|) of every
+# gradient comparison of the GPU tests; printed by tests/conftest.py at the end of the run
+GRAD_CHECKS = []
