@@ -13,9 +13,14 @@ Default workload = BASELINE.json configs[1]: DSEC training shape, per-rank batch
 Printed JSON line (rank 0): see the keys below; `value` = valid events of all ranks per second
 with inputs resident in HBM (CUDA events, max over ranks); `e2e` = same metric through the
 plugin API with pinned HOST inputs copied in (double-buffered) and the loss read back, every
-step inside the timed region; `roofline` = dominant kernel (by measured stage time) against
-the HBM peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port timed on the host
-cores on a bounded sample (one window).
+step inside the timed region - the host buffer is the loader-side `io.CompactEvents` (12 bytes
+per valid event, one cudaMemcpyAsync per step; built by the loader workers outside the step like
+the reference's own collate), `e2e_reference_layout` is the same leg on the reference's padded
+`[B, M, 6]` tensor; `train_step` = UNet(15, 2K) forward -> front end -> loss -> backward ->
+AdamW under DDP (NCCL all-reduce of the 31 M network gradients inside the timed region);
+`roofline` = dominant kernel (by measured stage time) against the HBM peak of
+MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port timed on the host cores on a bounded
+sample (one window).
 
 `--impl reference` times the reference's algorithm on the CPU (the oracle port: the reference
 is Python + pykeops and cannot run on the box) on the same config and metric.
@@ -217,6 +222,92 @@ def aggregate_over_ranks(ms_total, ms_e2e, n_valid, n_rows, dist, device):
 
 
 # ------------------------------------------------------------------------------------------
+# the network around the loss (stock PyTorch, as the north star prescribes): a 5-level UNet of
+# the shape of upstream src/models/unet/unet_model.py:6-36 (double 3x3 conv + BN + ReLU per level,
+# max-pool down, transposed-conv up, 64..1024 channels, 31.0 M parameters for 15 -> 2 channels)
+# ------------------------------------------------------------------------------------------
+def make_unet(n_in: int, n_out: int):
+    import torch.nn as nn
+
+    def block(ci, co):
+        return nn.Sequential(nn.Conv2d(ci, co, 3, padding=1, bias=False), nn.BatchNorm2d(co), nn.ReLU(inplace=True),
+                             nn.Conv2d(co, co, 3, padding=1, bias=False), nn.BatchNorm2d(co), nn.ReLU(inplace=True))
+
+    class UNet5(nn.Module):
+        def __init__(self):
+            super().__init__()
+            w = [64, 128, 256, 512, 1024]
+            self.enc = nn.ModuleList([block(n_in, w[0])] + [block(w[i], w[i + 1]) for i in range(4)])
+            self.pool = nn.MaxPool2d(2)
+            self.up = nn.ModuleList([nn.ConvTranspose2d(w[i + 1], w[i], 2, stride=2) for i in (3, 2, 1, 0)])
+            self.dec = nn.ModuleList([block(2 * w[i], w[i]) for i in (3, 2, 1, 0)])
+            self.head = nn.Conv2d(w[0], n_out, 1)
+
+        def forward(self, x):
+            skips = []
+            for i, e in enumerate(self.enc):
+                x = e(x if i == 0 else self.pool(x))
+                skips.append(x)
+            skips.pop()
+            for up, dec in zip(self.up, self.dec):
+                x = dec(torch.cat((skips.pop(), up(x)), 1))
+            return self.head(x)
+
+    return UNet5()
+
+
+def train_step_leg(args, dev, dist, world, local, cfg, w, L, times, ev_d, batch_keys, lib):
+    """One DSEC training step per iteration: UNet -> coeff grid -> trajectories -> CMax loss ->
+    backward -> (DDP: NCCL all-reduce of the network gradients, bucketed, overlapped with the
+    backward) -> AdamW.  scripts/flow_training.py:125-130, src/modules/trajectory_net.py:142-170."""
+    from motionpriorcmax_b200 import cabi, trajectories as tj
+    H, W = cfg["image_shape"]
+    B, K = w["B"], w["K"]
+    torch.manual_seed(1234)
+    net = make_unet(cfg["num_bins"], 2 * K).to(dev)
+    n_params = sum(p.numel() for p in net.parameters())
+    model = net
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(net, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)                # trajectory_net.py:213-219
+    voxel = torch.randn((B, cfg["num_bins"], H, W), device=dev)
+
+    def tstep():
+        opt.zero_grad(set_to_none=True)
+        cg = model(voxel)[:, None]                                       # [B, 1, 2K, H, W]
+        traj = tj.calculate_trajectories_at_t(cg, times, 4, K, w["basis"])
+        loss, _, _ = L.calc(traj, times, dict(batch_keys, events=ev_d))
+        loss.backward()
+        opt.step()
+        return loss
+
+    steps = max(1, min(args.steps, 10))
+    for _ in range(3):
+        tstep()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.cmax_stage_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tstep()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    st = cabi.stage_timing_read()
+    lib.cmax_stage_timing_enable(0)
+    loss_ms = sum(v[0] for v in st.values()) / steps
+    del model, net, opt, voxel
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "steps": steps, "loss_kernels_ms_per_step": loss_ms,
+            "network_parameters": n_params, "allreduce_bytes_per_step": n_params * 4 if world > 1 else 0}
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -314,94 +405,104 @@ def run_ours(args):
         packed = {"ms_total": ms_packed, "ms_pack": ms_pack,
                   "stage": {k: v[0] / v[1] for k, v in stage_p.items() if v[1] > 0}}
 
-    # ---- end-to-end arm: pinned host inputs, double-buffered H2D, loss read back ---------------
-    # events go through motionpriorcmax_b200.io.EventUploader: only the valid prefix of each
-    # polarity group crosses PCIe (the collate's zero padding is re-created on the device).
+    # ---- end-to-end arms: pinned host inputs, double-buffered H2D, loss read back ---------------
+    # (a) headline: the loader-side compact layout (io.CompactEvents: 12 B per valid event, built by
+    #     the loader workers outside the step) - ONE copy per step + the expand kernel;
+    # (b) the reference's own padded [B, M, 6] tensor through io.EventUploader (valid prefixes only).
+    from motionpriorcmax_b200 import io as cio
     from motionpriorcmax_b200.io import EventUploader
-    ev_p, cg_p = ev_h.pin_memory(), cg_h.pin_memory()
-    up = EventUploader(dev, n_buffers=2)
-    cg_bufs = [torch.empty_like(cg_d.detach()) for _ in range(2)]
-    cg_ready = [torch.cuda.Event(), torch.cuda.Event()]
-    pending = {}
+    cg_p = cg_h.pin_memory()
+    NBUF = 3            # two copies in flight / queued behind the step that computes (measured with
+                        # scripts/e2e_probe.py: with 2 buffers the copy of step i+1 waits for the slot of
+                        # step i-1 and the period is copy + part of the compute, with 3 it is the copy)
+    cg_bufs = [cg_d.detach().clone() for _ in range(NBUF)]
+    cg_ready = [torch.cuda.Event() for _ in range(NBUF)]
 
-    def prefetch(i):
-        buf, slot = up.upload(ev_p, npos)
-        with torch.cuda.stream(up.stream):
-            cg_bufs[i].copy_(cg_p, non_blocking=True)
-            cg_ready[i].record(up.stream)
-        pending[i] = (buf, slot)
-
-    def e2e_loop(k):
+    def run_e2e(upload, stream_of, wait, release, k, cg_from_host):
+        """Pipelined loop: the copies of steps i+1 and i+2 are queued while step i computes.
+        cg_from_host: also copy the coefficient grid (the NETWORK's output, 34 MB) in every step."""
         cur = torch.cuda.current_stream(dev)
-        prefetch(0)
+        pending = {}
+
+        def prefetch(j):
+            i = j % NBUF
+            buf, slot = upload()
+            with torch.cuda.stream(stream_of):
+                if cg_from_host:
+                    cg_bufs[i].copy_(cg_p, non_blocking=True)
+                cg_ready[i].record(stream_of)
+            pending[j] = (buf, slot)
+
+        for j in range(min(NBUF - 1, k)):
+            prefetch(j)
         out = 0.0
         for it in range(k):
-            i = it & 1
-            if it + 1 < k:
-                prefetch(i ^ 1)
-            buf, slot = pending.pop(i)
-            up.wait(slot, cur)
+            if it + NBUF - 1 < k:
+                prefetch(it + NBUF - 1)
+            buf, slot = pending.pop(it)
+            got = wait(slot, cur)                   # CompactUploader: the expanded PackedEvents
+            buf = buf if got is None else got
+            i = it % NBUF
             cur.wait_event(cg_ready[i])
             loss = step(cg_bufs[i].requires_grad_(), buf)
-            up.release(slot, cur)
+            release(slot, cur)
             out = loss.item()                       # D2H read of the step's result
             cg_bufs[i].requires_grad_(False)
         return out
 
-    ms_e2e = float("nan")
+    def time_e2e(upload, up, cg_from_host=False):
+        run_e2e(upload, up.stream, up.wait, up.release, 4, cg_from_host)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        run_e2e(upload, up.stream, up.wait, up.release, args.steps, cg_from_host)
+        f1.record()
+        barrier()
+        return f0.elapsed_time(f1)
+
+    ms_e2e = ms_e2e_ref = float("nan")
+    e2e_info = {}
     if not args.no_e2e:
-        e2e_loop(2)
+        t0 = time.perf_counter()
+        comp_h = cio.pack_events_compact(ev_h, npos, L)             # loader side, outside the step
+        pack_s = time.perf_counter() - t0
+        comp_p = comp_h.pin_memory()
+        cup = cio.CompactUploader(dev, L, n_buffers=NBUF)
+        ms_e2e = time_e2e(lambda: cup.upload(comp_p), cup)
+        ms_e2e_cg = time_e2e(lambda: cup.upload(comp_p), cup, cg_from_host=True)
+        # copy alone (no compute in flight): what PCIe gives this rank
         barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        e2e_loop(args.steps)
-        f1.record()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(cup.stream)
+        for _ in range(5):
+            _, sl = cup.upload(comp_p)
+            cup.release(sl, cup.stream)
+        c1.record(cup.stream)
         barrier()
-        ms_e2e = f0.elapsed_time(f1)
-    # ---- end-to-end arm on the packed host layout (built by the loader workers, outside the step) --
-    if packed is not None and not args.no_e2e and world == 1:      # host-side packing: rank-0-only leg
-        pk_h = cio.pack_events_native(ev_h, npos, L).pin_memory()      # C++ / OpenMP host packer (loader side)
-        pup = cio.PackedUploader(dev, n_buffers=2)
-        counts_h = pk_h.seg_start[:, -1].tolist()
-        ppending = {}
+        copy_ms = c0.elapsed_time(c1) / 5
+        e2e_info = {"h2d_bytes": int(cup.bytes_last), "host_issue_ms": cup.issue_ms_last,
+                    "copy_alone_ms": copy_ms, "host_pack_s_per_batch": pack_s,
+                    "cg_bytes": int(cg_p.numel() * 4), "ms_with_cg": ms_e2e_cg}
+        ev_p = ev_h.pin_memory()
+        up = EventUploader(dev, n_buffers=NBUF)
+        ms_e2e_ref = time_e2e(lambda: up.upload(ev_p, npos), up)
+        e2e_info["ref_h2d_bytes"] = int(up.bytes_last)
+        del ev_p
 
-        def pprefetch(i):
-            buf, slot = pup.upload(pk_h, counts_h)
-            with torch.cuda.stream(pup.stream):
-                cg_bufs[i].copy_(cg_p, non_blocking=True)
-                cg_ready[i].record(pup.stream)
-            ppending[i] = (buf, slot)
-
-        def pe2e_loop(k):
-            cur = torch.cuda.current_stream(dev)
-            pprefetch(0)
-            out = 0.0
-            for it in range(k):
-                i = it & 1
-                if it + 1 < k:
-                    pprefetch(i ^ 1)
-                buf, slot = ppending.pop(i)
-                pup.wait(slot, cur)
-                cur.wait_event(cg_ready[i])
-                loss = step(cg_bufs[i].requires_grad_(), buf)
-                pup.release(slot, cur)
-                out = loss.item()
-                cg_bufs[i].requires_grad_(False)
-            return out
-
-        pe2e_loop(2)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        pe2e_loop(args.steps)
-        f1.record()
-        barrier()
-        packed["ms_e2e"] = f0.elapsed_time(f1)
-        packed["h2d_bytes_per_step"] = int(pup.bytes_last + cg_p.numel() * 4)
+    # ---- training-step leg: the network and the DDP all-reduce around the loss ---------------------
+    train = None
+    if not args.no_train:
+        train = train_step_leg(args, dev, dist, world, local, cfg, w, L, times, ev_d, batch_keys, lib)
     clocks = sampler.stop()
 
     # ---- max over ranks -----------------------------------------------------------------------
     ms_total, ms_e2e, ev_all, rows_all = aggregate_over_ranks(ms_total, ms_e2e, n_valid, B * M, dist, dev)
+    extra = torch.tensor([ms_e2e_ref, train["ms_per_step"] if train else float("nan"),
+                          e2e_info.get("copy_alone_ms", float("nan")), e2e_info.get("host_issue_ms", float("nan"))],
+                         device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+    ms_e2e_ref, ms_train, copy_alone_ms, host_issue_ms = extra.tolist()
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -478,12 +579,43 @@ def run_ours(args):
                          "stage_ms_per_launch": per_launch,
                          "knn_worklist_cells": worklist},
             "e2e": {"value": e2e_val, "unit": "events/s",
-                    "h2d_bytes_per_step": int(up.bytes_last + cg_p.numel() * 4),
-                    "h2d_note": "valid event rows only (padding rows are zero-filled on the device)",
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                    "h2d_bytes_per_step": e2e_info.get("h2d_bytes", 0),
+                    "h2d_note": "the step's host input = the event windows the loader delivers, as io.CompactEvents: "
+                                "12 B per valid event + run tables, one cudaMemcpyAsync per step from pinned "
+                                "memory, expanded to 16-byte records on the device (cmax_expand_compact); built by "
+                                "the loader workers outside the step.  The coefficient grid is the network's "
+                                "output and stays on the device (see train_step); with_coeff_grid_from_host ships "
+                                "it over PCIe as well, every step",
+                    "with_coeff_grid_from_host": {
+                        "ms_per_step_rank0": e2e_info.get("ms_with_cg", float("nan")) / args.steps,
+                        "h2d_bytes_per_step": e2e_info.get("h2d_bytes", 0) + e2e_info.get("cg_bytes", 0)},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_GBps_per_rank_copy_alone": (e2e_info.get("h2d_bytes", 0) / (copy_alone_ms * 1e-3) / 1e9)
+                    if copy_alone_ms == copy_alone_ms else None,
+                    "copy_alone_ms": copy_alone_ms, "host_issue_ms_per_step": host_issue_ms,
+                    "host_pack_s_per_batch_rank0": e2e_info.get("host_pack_s_per_batch")},
+            "e2e_reference_layout": {
+                "value": ev_all / (ms_e2e_ref / args.steps * 1e-3), "unit": "events/s",
+                "ms_per_step": ms_e2e_ref / args.steps, "h2d_bytes_per_step": e2e_info.get("ref_h2d_bytes", 0),
+                "note": "the reference's padded [B, M, 6] tensor from pinned memory through io.EventUploader "
+                        "(valid prefixes only, one copy per window and polarity group)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if train is not None:
+            line["train_step"] = {
+                "what": "UNet(15, 2K) 31 M parameters (own definition of the shape of upstream "
+                        "src/models/unet/unet_model.py) -> front end -> CMax loss -> backward -> AdamW, per-rank "
+                        "batch %d, fp32 parameters, TF32 tensor-core convolutions (PyTorch default); under DDP the "
+                        "NCCL all-reduce of the network gradients is inside the timed region" % B,
+                "ms_per_step": ms_train, "steps": train["steps"],
+                "windows_per_s_all_ranks": world * B / (ms_train * 1e-3),
+                "events_per_s_all_ranks": ev_all / (ms_train * 1e-3),
+                "loss_kernels_ms_per_step_rank0": train["loss_kernels_ms_per_step"],
+                "loss_share_of_step": train["loss_kernels_ms_per_step"] / ms_train,
+                "network_parameters": train["network_parameters"],
+                "allreduce_bytes_per_step": train["allreduce_bytes_per_step"],
+                "collective": "torch DDP / NCCL all-reduce (bucketed, overlapped with backward)" if world > 1 else "none (1 GPU)"}
         if packed is not None:
             # per-rank numbers of rank 0 (ranks are independent; the headline keys above are max-over-ranks)
             ms_p = packed["ms_total"] / args.steps
@@ -495,13 +627,6 @@ def run_ours(args):
                 "device_pack_ms": packed["ms_pack"],
                 "value_rank0_with_device_pack_each_step": n_valid / ((ms_p + packed["ms_pack"]) * 1e-3),
                 "stage_ms_per_launch": packed["stage"]}
-            if "ms_e2e" in packed:
-                line["packed_layout"]["e2e"] = {
-                    "value_rank0": n_valid / (packed["ms_e2e"] / args.steps * 1e-3), "unit": "events/s",
-                    "ms_per_step": packed["ms_e2e"] / args.steps,
-                    "h2d_bytes_per_step": packed["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
-                    "note": "pinned host PackedEvents (io.pack_events_native / cmax_pack_events_host in the loader "
-                            "workers, outside the step) copied in every step, loss read back"}
         if world == 1 and not args.no_cpu:
             dt, n_ev = cpu_reference_step(cfg, w, cg_h, ev_h, npos)
             cores = os.cpu_count() or 1
@@ -550,7 +675,8 @@ def main():
                          "realistic atomic contention; SURVEY.md section 8d)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-packed", action="store_true", help="skip the packed-layout legs")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-input legs (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the UNet + DDP training-step leg")
     ap.add_argument("--prof-warmup", type=int, default=None, help="override the >=3 warm-up rule (ncu runs only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -133,6 +133,25 @@ int cmax_pack_events_host(const CmaxConfig *cfg, const float *events_host, int64
                           int64_t num_pos_events, float *records_host, int64_t records_stride,
                           int32_t *seg_start_host, int64_t *skipped_host);
 
+/* Compact WIRE layout for the host -> device copy (12 bytes per valid event instead of 24 / 16):
+ *   coords     [T, 3] float32 (y, x, t): the windows of the batch back to back, no padding rows;
+ *              window b owns rows sample_off[b] .. sample_off[b + 1] (int64 [B + 1]);
+ *   fine_start [B, G * NT * nb + 1] int32: per window, prefix offsets (relative to its first row)
+ *              of the runs ordered by (polarity group, source tile, time bin): the bin column of
+ *              the reference layout (focus.py:185) is implied by the run, the LUT cell by (y, x).
+ * cmax_pack_events_host_compact (HOST pointers, C++ / OpenMP, for the loader workers): call once
+ *   with coords_host = NULL to get fine_start and sample_off (sizes), then with a buffer of at
+ *   least sample_off[B] rows.  cmax_expand_compact (DEVICE pointers): one kernel rebuilds the
+ *   16-byte records [B, records_stride, 4] and seg_start [B, G * NT + 1] of the packed layout,
+ *   records_stride >= the largest window; LUT cells recomputed with the reference's arithmetic. */
+int cmax_pack_events_host_compact(const CmaxConfig *cfg, const float *events_host, int64_t B, int64_t M,
+                                  int64_t num_pos_events, float *coords_host, int64_t coords_capacity,
+                                  int32_t *fine_start_host, int64_t *sample_off_host,
+                                  int64_t *skipped_host);
+int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_t *fine_start,
+                        const int64_t *sample_off, int64_t B, int64_t records_stride,
+                        float *records_out, int32_t *seg_start_out, void *stream);
+
 /* cmax_forward / cmax_backward on the packed layout: same outputs, same workspace
  * (cmax_workspace_bytes(cfg, B, M, n) with the M of `records`).  The event stage accumulates
  * the IWE votes of a (tile, group) segment in a shared-memory window and flushes once; votes

@@ -27,6 +27,7 @@ EXPORTS = (
     "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
     "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
     "cmax_backward_accumulate", "cmax_backward_finish", "cmax_pack_events_host",
+    "cmax_pack_events_host_compact", "cmax_expand_compact",
 )
 
 
@@ -72,6 +73,11 @@ def load():
     lib.cmax_pack_events.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, P, P, P, P]
     lib.cmax_pack_events_host.restype = c_int32
     lib.cmax_pack_events_host.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, c_int64, P, P]
+    lib.cmax_pack_events_host_compact.restype = c_int32
+    lib.cmax_pack_events_host_compact.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, c_int64,
+                                                  P, P, P]
+    lib.cmax_expand_compact.restype = c_int32
+    lib.cmax_expand_compact.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, P, P, P]
     lib.cmax_forward_packed.restype = c_int32
     lib.cmax_forward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
                                         P, P, P, P, c_size_t, P]

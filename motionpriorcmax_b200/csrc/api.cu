@@ -101,6 +101,9 @@ int make_geom(const CmaxConfig *c, int64_t B, int64_t M, int64_t n, int64_t npos
     if (c->num_tref != 1 && (c->scale_iwe_by_dt || c->polarity_aware_batching ||
                              c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT))
         return CMAX_ERR_BAD_CONFIG;
+    // focus.py:170 builds flow_to_next only for smooth_weight > 0, and calculate_smooth_loss (:232-246)
+    // then dereferences None for a negative weight: the reference crashes on this combination
+    if (c->smooth_type == CMAX_SMOOTH_ON_FLOW_TO_NEXT && c->smooth_weight < 0.0f) return CMAX_ERR_BAD_CONFIG;
     if (B < 1 || M < 0 || n < 1) return CMAX_ERR_BAD_SHAPE;
     if (c->num_knn > n) return CMAX_ERR_BAD_SHAPE;
     if (c->polarity_aware_batching && (npos < 0 || npos > M)) return CMAX_ERR_BAD_SHAPE;
@@ -540,6 +543,22 @@ int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int6
     if (((uintptr_t)records_out & 15u)) return CMAX_ERR_WORKSPACE;
     return launch_pack_events(g, events, reinterpret_cast<float4 *>(records_out), seg_start_out, scratch,
                               reinterpret_cast<long long *>(skipped_out), static_cast<cudaStream_t>(stream));
+}
+
+int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_t *fine_start,
+                        const int64_t *sample_off, int64_t B, int64_t records_stride,
+                        float *records_out, int32_t *seg_start_out, void *stream)
+{
+    Geom g;
+    int rc = make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if ((rc = pack_supported(g))) return rc;
+    if (!fine_start || !sample_off || !seg_start_out || (records_stride > 0 && (!coords || !records_out)))
+        return CMAX_ERR_BAD_SHAPE;
+    if (((uintptr_t)records_out & 15u)) return CMAX_ERR_WORKSPACE;
+    return launch_expand_compact(g, coords, fine_start, reinterpret_cast<const long long *>(sample_off),
+                                 records_stride, reinterpret_cast<float4 *>(records_out), seg_start_out,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,

@@ -76,6 +76,9 @@ int launch_event_backward(const Geom &g, const Layout &L, const float *events, c
                           const float *grad_loss, char *ws, cudaStream_t st, int phase = 0);
 int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
                        int *scratch, long long *skipped, cudaStream_t st);
+int launch_expand_compact(const Geom &g, const float *coords, const int *fine_start,
+                          const long long *sample_off, int64_t Mp, float4 *records, int *seg_start,
+                          cudaStream_t st);
 int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
                                 const int *seg_start, const float *times, char *ws, cudaStream_t st);
 int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *records,

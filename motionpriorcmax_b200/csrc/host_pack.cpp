@@ -128,3 +128,72 @@ extern "C" int cmax_pack_events_host(const CmaxConfig *cfg, const float *events_
     }
     return rc;
 }
+
+
+// Compact wire layout (12 bytes per valid event instead of 16 / 24): what crosses PCIe every step.
+//   coords     [T, 3] float32 (y, x, t), the windows of the batch back to back (no padding):
+//              window b owns rows sample_off[b] .. sample_off[b + 1];
+//   fine_start [B, G * NT * nb + 1] int32: per window, prefix offsets (relative to the window's
+//              first row) of the runs ordered by (polarity group, source tile, time bin) - the
+//              time bin (focus.py:185: it = int(bin)) is implied by the run, the LUT cell by (y, x).
+// cmax_expand_compact (device) turns it into the 16-byte records + seg_start of the packed layout.
+// Same stable counting sort as above with the finer key; rows keep their order inside a run.
+extern "C" int cmax_pack_events_host_compact(const CmaxConfig *cfg, const float *events_host, int64_t B,
+                                             int64_t M, int64_t num_pos_events, float *coords_host,
+                                             int64_t coords_capacity, int32_t *fine_start_host,
+                                             int64_t *sample_off_host, int64_t *skipped_host)
+{
+    HostLayout L;
+    if (!cfg) return CMAX_ERR_BAD_CONFIG;
+    if (!host_layout(cfg, &L)) return CMAX_ERR_UNSUPPORTED;
+    if (B < 0 || M < 0 || (!events_host && B * M > 0) || !fine_start_host || !sample_off_host) return CMAX_ERR_BAD_SHAPE;
+    if (L.G == 2 && (num_pos_events < 0 || num_pos_events > M)) return CMAX_ERR_BAD_SHAPE;
+    if (M > (int64_t)INT32_MAX) return CMAX_ERR_UNSUPPORTED;
+    const int nkeys = L.G * L.nt * L.nb;
+    int64_t dropped = 0, odd = 0;
+    const bool fill = coords_host != nullptr;       // second call: sample_off_host is an input
+    if (fill && sample_off_host[B] > coords_capacity) return CMAX_ERR_BAD_SHAPE;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : dropped, odd)
+    for (int64_t b = 0; b < B; ++b) {
+        const float *ev = events_host + b * M * 6;
+        int32_t *seg = fine_start_host + b * (int64_t)(nkeys + 1);
+        std::vector<int32_t> key((size_t)M);
+        std::vector<int32_t> cursor((size_t)nkeys + 1, 0);
+        for (int64_t m = 0; m < M; ++m) {
+            uint32_t mw = 0;
+            int k = row_key(ev + m * 6, m, num_pos_events, L, &mw);
+            if (k >= 0) {
+                k = k * L.nb + (int)(mw >> 24);
+                ++cursor[(size_t)k + 1];
+                if (ev[m * 6 + 5] != 1.0f) ++odd;
+            } else if (k == -2) {
+                ++dropped;
+                if (ev[m * 6 + 5] != 1.0f) ++odd;
+            }
+            key[(size_t)m] = k;
+        }
+        for (int k = 0; k < nkeys; ++k) cursor[(size_t)k + 1] += cursor[(size_t)k];
+        memcpy(seg, cursor.data(), sizeof(int32_t) * (size_t)(nkeys + 1));
+        if (fill) {
+            float *rec = coords_host + sample_off_host[b] * 3;
+            for (int64_t m = 0; m < M; ++m) {
+                const int k = key[(size_t)m];
+                if (k < 0) continue;
+                float *dst = rec + (int64_t)cursor[(size_t)k]++ * 3;
+                dst[0] = ev[m * 6 + 0];
+                dst[1] = ev[m * 6 + 1];
+                dst[2] = ev[m * 6 + 2];
+            }
+        }
+    }
+    if (!fill) {                                     // first call: window offsets from the counts
+        sample_off_host[0] = 0;
+        for (int64_t b = 0; b < B; ++b)
+            sample_off_host[b + 1] = sample_off_host[b] + fine_start_host[b * (int64_t)(nkeys + 1) + nkeys];
+    }
+    if (skipped_host) {
+        skipped_host[0] = dropped;
+        skipped_host[1] = odd;
+    }
+    return CMAX_OK;
+}

@@ -204,6 +204,51 @@ pack_scatter_kernel(const float *__restrict__ events, Geom g, int *__restrict__ 
                 make_float4(ry[u], rx[u], rt[u], __uint_as_float(meta[u]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// compact wire layout (12 B per event, host packed) -> packed records + seg_start
+// ---------------------------------------------------------------------------------------------
+// One thread per record: the run it sits in (binary search in the window's fine_start table, which
+// stays in L1 / L2: 36 KB per DSEC window) gives the time bin, (y, x) give the LUT cell with the
+// reference's own float floor division (focus.py:186-187), exactly what the packers store in `meta`.
+__global__ void __launch_bounds__(256)
+expand_compact_kernel(const float *__restrict__ coords, const int *__restrict__ fine_start,
+                      const long long *__restrict__ sample_off, Geom g, int64_t Mp,
+                      float4 *__restrict__ records, int *__restrict__ seg_start)
+{
+    const int b = blockIdx.y;
+    const int F = g.P * g.nt * g.nb;
+    const int *fs = fine_start + (int64_t)b * (F + 1);
+    const int count = __ldg(fs + F);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= g.P * g.nt)                                   // coarse table: every nb-th fine entry
+        seg_start[(int64_t)b * (g.P * g.nt + 1) + i] = __ldg(fs + i * g.nb);
+    if (i >= count) return;
+    int lo = 0, hi = F - 1;                                // last run whose start is <= i
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(fs + mid) <= (int)i) lo = mid; else hi = mid - 1;
+    }
+    const int bin = lo % g.nb;
+    const float *c = coords + (__ldg(sample_off + b) + i) * 3;
+    const float y = __ldg(c), x = __ldg(c + 1), t = __ldg(c + 2);
+    const float fsz = (float)g.s;
+    const int iy = (int)floordiv_f32(y, fsz), ix = (int)floordiv_f32(x, fsz);
+    const unsigned meta = ((unsigned)bin << 24) | ((unsigned)iy << 12) | (unsigned)ix;
+    records[(int64_t)b * Mp + i] = make_float4(y, x, t, __uint_as_float(meta));
+}
+
+int launch_expand_compact(const Geom &g, const float *coords, const int *fine_start,
+                          const long long *sample_off, int64_t Mp, float4 *records, int *seg_start,
+                          cudaStream_t st)
+{
+    const int64_t span = Mp > g.P * g.nt + 1 ? Mp : g.P * g.nt + 1;
+    dim3 grid((unsigned)((span + 255) / 256), (unsigned)g.B);
+    StageScope sc(ST_PACK, st);
+    count_launch();
+    expand_compact_kernel<<<grid, 256, 0, st>>>(coords, fine_start, sample_off, g, Mp, records, seg_start);
+    return check_launch();
+}
+
 int launch_pack_events(const Geom &g, const float *events, float4 *records, int *seg_start,
                        int *scratch, long long *skipped, cudaStream_t st)
 {

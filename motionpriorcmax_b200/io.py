@@ -12,6 +12,13 @@ tile-binned event layout"): 16-byte records of the valid events only, grouped by
 and 32x32-pixel source tile, so the event kernels accumulate in shared memory.  Build it in the
 loader workers with `pack_events_host` (torch CPU ops, no GPU) or on the device with
 `pack_events` (C ABI `cmax_pack_events`); pass it as `batch['events']` to `FocusLoss.calc`.
+
+`CompactEvents` is the WIRE form of the same layout for the host -> device copy: 12 bytes per valid
+event ((y, x, t) float32; the time bin is implied by the run an event sits in, the LUT cell by its
+coordinates), all windows of a batch back to back in ONE pinned buffer, so a step's events cross
+PCIe in one `cudaMemcpyAsync`.  `pack_events_compact` builds it in the loader workers (C++ /
+OpenMP), `CompactUploader` copies it (double buffered) and rebuilds the 16-byte records on the
+device with one kernel (`cmax_expand_compact`); `FocusLoss.calc` also accepts it directly.
 """
 from __future__ import annotations
 
@@ -331,6 +338,153 @@ class PackedUploader:
 
     def wait(self, slot: int, stream=None):
         (stream or torch.cuda.current_stream(self.device)).wait_event(self.ready[slot])
+
+    def release(self, slot: int, stream=None):
+        self.free[slot].record(stream or torch.cuda.current_stream(self.device))
+
+
+# ------------------------------------------------------------------------------------------------
+# compact wire layout: 12 B per valid event, one buffer per batch
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class CompactEvents:
+    """coords [T, 3] float32 (y, x, t), fine_start [B, G*NT*nb + 1] int32, sample_off [B + 1] int64;
+    see include/cmax_b200.h ("Compact WIRE layout").  `max_count` = largest window (host int)."""
+    coords: torch.Tensor
+    fine_start: torch.Tensor
+    sample_off: torch.Tensor
+    max_count: int
+    skipped: Optional[torch.Tensor] = None
+
+    @property
+    def is_cuda(self):
+        return self.coords.is_cuda
+
+    @property
+    def device(self):
+        return self.coords.device
+
+    def num_events(self) -> torch.Tensor:
+        return self.fine_start[:, -1]
+
+    def nbytes(self) -> int:
+        return int(self.coords.numel() * 4 + self.fine_start.numel() * 4 + self.sample_off.numel() * 8)
+
+    def to(self, device, non_blocking: bool = False):
+        return CompactEvents(self.coords.to(device, non_blocking=non_blocking),
+                             self.fine_start.to(device, non_blocking=non_blocking),
+                             self.sample_off.to(device, non_blocking=non_blocking), self.max_count, self.skipped)
+
+    def pin_memory(self):
+        return CompactEvents(self.coords.pin_memory(), self.fine_start.pin_memory(),
+                             self.sample_off.pin_memory(), self.max_count, self.skipped)
+
+
+def pack_events_compact(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
+                        strict: bool = True) -> CompactEvents:
+    """Loader-side builder of the compact wire layout from an upstream-layout `[B, M, 6]` CPU tensor
+    (`cmax_pack_events_host_compact`: C++ / OpenMP stable counting sort, one thread per window)."""
+    from . import cabi
+    import ctypes
+    lib = cabi.load()
+    cfg = _cfg_of(loss_or_cfg)
+    ev = events.detach().to(torch.float32).cpu().contiguous()
+    B, M, six = ev.shape
+    assert six == 6, "events must be [B, M, 6]"
+    _, nty, ntx, G = cabi.pack_layout(cfg)
+    F = G * nty * ntx * cfg.num_bins
+    npos = int(num_pos_events) if (cfg.polarity_aware_batching and num_pos_events is not None) else 0
+    fine = torch.empty((B, F + 1), dtype=torch.int32)
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    skipped = torch.zeros(2, dtype=torch.int64)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())             # noqa: E731
+    cabi.check(lib.cmax_pack_events_host_compact(cfg, p(ev), B, M, npos, None, 0, p(fine), p(off), p(skipped)),
+               "cmax_pack_events_host_compact")
+    _check_binary_valid(int(skipped[1]), strict)
+    T = int(off[-1])
+    coords = torch.empty((max(T, 1), 3), dtype=torch.float32)
+    cabi.check(lib.cmax_pack_events_host_compact(cfg, p(ev), B, M, npos, p(coords), coords.shape[0], p(fine),
+                                                 p(off), p(skipped)), "cmax_pack_events_host_compact")
+    return CompactEvents(coords, fine, off, max(int(fine[:, -1].max()) if B else 0, 1), skipped)
+
+
+def expand_compact(compact: CompactEvents, loss_or_cfg, out: Optional[PackedEvents] = None) -> PackedEvents:
+    """Device: compact wire layout -> `PackedEvents` (one kernel, on the current stream)."""
+    from . import cabi
+    lib = cabi.load()
+    cfg = _cfg_of(loss_or_cfg)
+    if not compact.is_cuda:
+        raise RuntimeError("expand_compact needs CUDA tensors (CompactEvents.to(device) first)")
+    dev = compact.device
+    B = compact.fine_start.shape[0]
+    _, nty, ntx, G = cabi.pack_layout(cfg)
+    Mp = int(compact.max_count)
+    if out is None or out.records.shape[0] != B or out.records.shape[1] < Mp:
+        out = PackedEvents(torch.empty((B, Mp, 4), dtype=torch.float32, device=dev),
+                           torch.empty((B, G * nty * ntx + 1), dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        cabi.check(lib.cmax_expand_compact(cfg, cabi.ptr(compact.coords), cabi.ptr(compact.fine_start),
+                                           cabi.ptr(compact.sample_off), B, out.records.shape[1],
+                                           cabi.ptr(out.records), cabi.ptr(out.seg_start),
+                                           cabi.stream_ptr(dev)), "cmax_expand_compact")
+    return out
+
+
+class CompactUploader:
+    """Double-buffered H2D staging of `CompactEvents` batches: ONE copy of `12 B x events` (plus two
+    small tables) from pinned memory on a copy stream; `wait(slot)` makes the consumer's stream wait
+    for it and returns the device `PackedEvents` rebuilt there by the expand kernel."""
+
+    def __init__(self, device, loss_or_cfg, n_buffers: int = 2):
+        self.device = torch.device(device)
+        self.cfg = _cfg_of(loss_or_cfg)
+        self.stream = torch.cuda.Stream(self.device)
+        self.n = n_buffers
+        self.wire = [None] * n_buffers           # device CompactEvents buffers (capacity may exceed use)
+        self.out = [None] * n_buffers            # device PackedEvents buffers
+        self.ready = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.free = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.turn = 0
+        self.bytes_last = 0
+        self.issue_ms_last = 0.0                 # host time spent issuing the copies + the kernel
+        for ev in self.free:
+            ev.record(torch.cuda.current_stream(self.device))
+
+    def upload(self, compact: CompactEvents):
+        import time
+        assert compact.coords.is_pinned() and compact.fine_start.is_pinned() and compact.sample_off.is_pinned()
+        t0 = time.perf_counter()
+        slot = self.turn
+        self.turn = (self.turn + 1) % self.n
+        T = int(compact.sample_off[-1])
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[slot])
+            w = self.wire[slot]
+            if w is None or w.coords.shape[0] < max(T, 1) or w.fine_start.shape != compact.fine_start.shape:
+                cap = max(int(T * 1.25), 1)
+                w = CompactEvents(torch.empty((cap, 3), dtype=torch.float32, device=self.device),
+                                  torch.empty(compact.fine_start.shape, dtype=torch.int32, device=self.device),
+                                  torch.empty(compact.sample_off.shape, dtype=torch.int64, device=self.device), 0)
+                self.wire[slot] = w
+            if T:
+                w.coords[:T].copy_(compact.coords[:T], non_blocking=True)       # the one big copy
+            w.fine_start.copy_(compact.fine_start, non_blocking=True)
+            w.sample_off.copy_(compact.sample_off, non_blocking=True)
+            w.max_count = compact.max_count
+            self.bytes_last = T * 12 + compact.fine_start.numel() * 4 + compact.sample_off.numel() * 8
+            self.ready[slot].record(self.stream)
+        self.issue_ms_last = (time.perf_counter() - t0) * 1e3
+        return w, slot
+
+    def wait(self, slot: int, stream=None) -> PackedEvents:
+        """Make `stream` (default: the current one) wait for the slot's copy, then rebuild the
+        16-byte records there (the expand kernel runs on the CONSUMER's stream: on the copy stream
+        it would queue behind the consumer's long kernels and hold up the next copy)."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        stream.wait_event(self.ready[slot])
+        with torch.cuda.stream(stream):
+            self.out[slot] = expand_compact(self.wire[slot], self.cfg, self.out[slot])
+        return self.out[slot]
 
     def release(self, slot: int, stream=None):
         self.free[slot].record(stream or torch.cuda.current_stream(self.device))

@@ -64,11 +64,13 @@ def _assert_grad_close(got, truth64, cfg, traj, times, ev, npos, tol=2 * TOL, gp
     o.forward(traj, times, ev, npos)
     dx0, dy0 = np.array(o.ctx["dx"]), np.array(o.ctx["dy"])
     dx, dy = fo.sobel(np.asarray(gpu_iwes, np.float64).reshape(o.ctx["dx"].shape))
-    flipped = (np.sign(dx) != np.sign(dx0)) | (np.sign(dy) != np.sign(dy0))
+    fx, fy = np.sign(dx) != np.sign(dx0), np.sign(dy) != np.sign(dy0)
+    flipped = fx | fy
     n_flip = int(flipped.sum())
     scale = float(np.mean(np.abs(dx0)) + np.mean(np.abs(dy0))) / 2 + 1e-300
-    worst = float(max(np.abs(dx0[flipped]).max(initial=0.0), np.abs(dy0[flipped]).max(initial=0.0),
-                      np.abs(dx[flipped]).max(initial=0.0), np.abs(dy[flipped]).max(initial=0.0))) / scale
+    # the response that flipped, in either evaluation (the other component of the pixel may be large)
+    worst = float(max(np.abs(dx0[fx]).max(initial=0.0), np.abs(dx[fx]).max(initial=0.0),
+                      np.abs(dy0[fy]).max(initial=0.0), np.abs(dy[fy]).max(initial=0.0))) / scale
     assert n_flip <= max(1e-3 * flipped.size, 2), (n_flip, flipped.size, e64)
     assert worst <= 1e-4, (worst, n_flip, e64)
     o.ctx["dx"], o.ctx["dy"] = dx, dy

@@ -175,6 +175,49 @@ def test_pack_layout_query_and_limits():
 # ------------------------------------------------------------------------------------------
 # GPU
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s,pab", [(4, True), (3, False), (16, True)])
+def test_compact_host_packer_layout_contract(s, pab):
+    """cmax_pack_events_host_compact (host pointers only): every (group, tile, bin) run holds exactly
+    the rows of the reference layout that belong there, in their original order; 12 bytes per row;
+    the windows sit back to back in one buffer; same drop counters as the 16-byte packer."""
+    from motionpriorcmax_b200 import cabi, io, synthetic
+    H, W, nb = 120, 150, 9
+    d = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(H, W), num_bins=nb, lut_superpixel_size=s,
+             num_knn=2, polarity_aware_batching=pab)
+    cfg = _cfg(d)
+    ct, nty, ntx, G = cabi.pack_layout(cfg)
+    ev, npos = synthetic.make_event_batch(4, [9000, 4000, 0, 12000], H, W, nb, pab, seed=6)
+    ev = ev.clone()
+    ev[0, 400:450, 1] = -0.25                  # outside the table
+    ev[1, :30, 4] = float(nb)                  # bin out of range
+    ev[1, 40, 0] = float("nan")
+    c = io.pack_events_compact(ev, npos, cfg)
+    ref = io.pack_events_native(ev, npos, cfg)
+    assert c.skipped.tolist() == ref.skipped.tolist()
+    assert c.coords.shape[1] == 3 and c.coords.dtype == torch.float32
+    assert c.sample_off.tolist() == [0] + torch.cumsum(ref.seg_start[:, -1].long(), 0).tolist()
+    assert torch.equal(c.fine_start[:, ::nb], ref.seg_start)              # coarse table = 16-byte layout's
+    assert c.max_count == int(ref.seg_start[:, -1].max())
+    Hq, Wq = -(-H // s), -(-W // s)
+    e = ev.numpy()
+    for b in range(4):
+        it = e[b, :, 4]
+        ok = (e[b, :, 5] != 0) & (it == it) & (np.trunc(np.nan_to_num(it)) >= 0) & (np.trunc(np.nan_to_num(it)) < nb)
+        fy, fx = (torch.as_tensor(e[b, :, 0]) // s).numpy(), (torch.as_tensor(e[b, :, 1]) // s).numpy()
+        ok &= (fy >= 0) & (fy < Hq) & (fx >= 0) & (fx < Wq)
+        grp = (np.arange(e.shape[1]) >= npos).astype(np.int64) if pab else np.zeros(e.shape[1], np.int64)
+        key = np.where(ok, (grp * nty * ntx + (np.nan_to_num(fy).astype(np.int64) // ct) * ntx
+                            + np.nan_to_num(fx).astype(np.int64) // ct) * nb
+                       + np.trunc(np.nan_to_num(it)).astype(np.int64), -1)
+        base = int(c.sample_off[b])
+        fs = c.fine_start[b].numpy()
+        for k in np.unique(key[key >= 0]):
+            rows = e[b, key == k, :3]                                     # original order
+            got = c.coords[base + fs[k]:base + fs[k + 1]].numpy()
+            assert got.shape == rows.shape and np.array_equal(got.view(np.uint32), rows.view(np.uint32)), (b, k)
+        assert fs[-1] == int((key >= 0).sum())
+
+
 def _cuda():
     assert torch.cuda.is_available(), "these tests need a GPU (run with -m gpu on a B200)"
     return torch.device("cuda:0")
@@ -194,6 +237,8 @@ def _run(cfg, traj, times, events, npos, mode, deterministic=False):
             batch["num_pos_events"] = npos
     elif mode == "packed_dev":
         batch = {"events": io.pack_events(ev.to(dev), npos if npos >= 0 else None, L)}
+    elif mode == "compact":      # 12-byte wire layout, expanded on the device inside calc
+        batch = {"events": io.pack_events_compact(ev, npos if npos >= 0 else None, L).to(dev)}
     else:
         batch = {"events": io.pack_events_host(ev, npos if npos >= 0 else None, L).to(dev)}
     loss, log, misc = L.calc(t, torch.as_tensor(times, device=dev), batch, return_flow_lut=True)
@@ -206,7 +251,7 @@ def _run(cfg, traj, times, events, npos, mode, deterministic=False):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", LOSS_CASES)
-@pytest.mark.parametrize("mode", ["packed_dev", "packed_host"])
+@pytest.mark.parametrize("mode", ["packed_dev", "packed_host", "compact"])
 def test_packed_matches_reference_golden(name, mode):
     from test_gpu_parity import _assert_grad_close
     c = load_case(name)
@@ -225,11 +270,45 @@ def test_packed_deterministic_is_bit_identical_to_unpacked(name):
     kernels must reproduce the unpacked kernels bit for bit (IWE, loss, gradients)."""
     c = load_case(name)
     a = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], "plain", True)
-    for mode in ("packed_dev", "packed_host"):
+    for mode in ("packed_dev", "packed_host", "compact"):
         b = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], mode, True)
         assert a["loss"] == b["loss"] and a["focus"] == b["focus"]
         assert np.array_equal(a["iwes"], b["iwes"])
         assert np.array_equal(a["dtraj"], b["dtraj"])
+
+
+@pytest.mark.gpu
+def test_compact_expands_to_the_host_packed_layout():
+    """cmax_expand_compact: the 16-byte records rebuilt on the device from the 12-byte wire layout
+    are, segment by segment, the records of the host packer (bit for bit: the LUT cell in `meta`
+    is recomputed with the reference's float floor division), through the uploader too."""
+    from motionpriorcmax_b200 import cabi, io, synthetic
+    dev = _cuda()
+    for d, B, M in ((dict(synthetic.DSEC_LOSS_CONFIG), 3, [150_000, 40_000, 0]),
+                    (dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(50, 70), lut_superpixel_size=3,
+                          polarity_aware_batching=False, num_bins=5, num_knn=2), 2, [5000, 7000])):
+        cfg = _cfg(d)
+        H, W = d["image_shape"]
+        ev, npos = synthetic.make_event_batch(B, M, H, W, d["num_bins"], d["polarity_aware_batching"], seed=8)
+        ev = ev.clone()
+        k = 300                                # coordinates a few ulp around cell edges
+        s = d["lut_superpixel_size"]
+        rng = np.random.default_rng(2)
+        edge = (rng.integers(0, H // s, k) * s).astype(np.float32)
+        ev[0, :k, 0] = torch.as_tensor(edge + rng.choice(np.array([-2e-6, -1e-6, 0, 1e-6, 1e-5], np.float32), k)).clamp_(0)
+        layout = cabi.pack_layout(cfg)
+        host = io.pack_events_native(ev, npos, cfg)
+        comp = io.pack_events_compact(ev, npos, cfg)
+        a = io.expand_compact(comp.to(dev), cfg)
+        up = io.CompactUploader(dev, cfg)
+        _, slot = up.upload(comp.pin_memory())
+        b = up.wait(slot)
+        torch.cuda.synchronize()
+        assert up.bytes_last == 12 * int(comp.sample_off[-1]) + comp.fine_start.numel() * 4 + comp.sample_off.numel() * 8
+        for got in (a, b):
+            assert torch.equal(host.seg_start, got.seg_start.cpu())
+            assert _segments(host, layout) == _segments(
+                io.PackedEvents(got.records[:, :host.records.shape[1]], got.seg_start), layout)
 
 
 @pytest.mark.gpu
