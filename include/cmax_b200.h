@@ -254,7 +254,9 @@ int cmax_dense_flow(const float *traj_flow, const int64_t *pixel_positions, int6
 
 /* Micro-benchmark used by bench.py to measure the atomic side of the roofline on the box:
  * n_ops float32 `red.global.add` to pseudo-random addresses inside `region_floats` floats.
- * mode 0: global red.f32, 1: shared-memory atomics + flush, 2: global red on int64. */
+ * mode 0: global red.f32, 1: shared-memory atomics + flush, 2: global red on int64,
+ * 3: red.global.add.v2.f32 (n_ops / 2 requests: the two x-adjacent corners of a vote per request),
+ * 4: red.global.add.v4.f32 (n_ops / 2 requests: the corner pair in the middle of an aligned quad). */
 int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, int32_t mode,
                            void *stream);
 

@@ -317,6 +317,18 @@ atomic_bench_kernel(float *region, unsigned region_floats, int64_t n_ops)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n_ops; i += stride) {
         unsigned h = hash32((unsigned)i * 2654435761u + 12345u);
+        if (MODE == 3 || MODE == 4) {
+            // vector reds as event_forward issues them: one request per image row of the vote
+            // (MODE 3: the two x-adjacent corners as red.v2 on an 8-byte aligned pair; MODE 4: the
+            // pair in the middle of a 16-byte aligned quad as red.v4 with zeros in the outer lanes)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                unsigned a = (h % (region_floats - 644u)) + k * 640u;
+                if (MODE == 3) red_add_f32x2(region + (a & ~1u), 1.0f, 1.0f);
+                else red_add_f32x4(region + (a & ~3u), 0.0f, 1.0f, 1.0f, 0.0f);
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // mimic a bilinear vote: (p, p+1, p+W, p+W+1) with W = 640
@@ -370,6 +382,7 @@ int cmax_forward(const CmaxConfig *cfg, const float *trajectories, const float *
                  float *iwes_out, float *losses_out, float *flow_lut_out, void *workspace,
                  size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
     if (rc != CMAX_OK) return rc;
@@ -394,6 +407,7 @@ int cmax_backward(const CmaxConfig *cfg, const float *trajectories, const float 
                   const float *grad_loss, float *dtraj_out, void *workspace,
                   size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
     if (rc != CMAX_OK) return rc;
@@ -438,6 +452,7 @@ int cmax_forward_accumulate(const CmaxConfig *cfg, const float *trajectories, co
                             int64_t num_pos_events, float *flow_lut_out, void *workspace,
                             size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
     if (rc != CMAX_OK) return rc;
@@ -455,6 +470,7 @@ int cmax_forward_accumulate(const CmaxConfig *cfg, const float *trajectories, co
 int cmax_forward_finish(const CmaxConfig *cfg, int64_t B, int64_t M, int64_t n, float *iwes_out,
                         float *losses_out, void *workspace, size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, 0, &g);
     if (rc != CMAX_OK) return rc;
@@ -475,6 +491,7 @@ int cmax_backward_accumulate(const CmaxConfig *cfg, const float *trajectories, c
                              int64_t num_pos_events, const float *grad_loss, int32_t include_smooth,
                              void *workspace, size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, num_pos_events, &g);
     if (rc != CMAX_OK) return rc;
@@ -496,6 +513,7 @@ int cmax_backward_finish(const CmaxConfig *cfg, const float *trajectories, int64
                          int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
                          size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, 0, &g);
     if (rc != CMAX_OK) return rc;
@@ -535,6 +553,7 @@ int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int6
                      int64_t num_pos_events, float *records_out, int32_t *seg_start_out,
                      int32_t *scratch, int64_t *skipped_out, void *stream)
 {
+    DeviceGuard dev_guard(seg_start_out);
     Geom g;
     int rc = make_geom(cfg, B, M, cfg ? cfg->num_knn : 1, num_pos_events, &g);
     if (rc != CMAX_OK) return rc;
@@ -549,6 +568,7 @@ int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_
                         const int64_t *sample_off, int64_t B, int64_t records_stride,
                         float *records_out, int32_t *seg_start_out, void *stream)
 {
+    DeviceGuard dev_guard(seg_start_out);
     Geom g;
     int rc = make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g);
     if (rc != CMAX_OK) return rc;
@@ -566,6 +586,7 @@ int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const 
                         int64_t n, float *iwes_out, float *losses_out, float *flow_lut_out,
                         void *workspace, size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, 0, &g);
     if (rc != CMAX_OK) return rc;
@@ -593,6 +614,7 @@ int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const
                          int64_t n, const float *grad_loss, float *dtraj_out, void *workspace,
                          size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = make_geom(cfg, B, M, n, 0, &g);
     if (rc != CMAX_OK) return rc;
@@ -615,6 +637,7 @@ int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_
                     int64_t row_stride, int32_t H, int32_t W, float sigma, float *out,
                     float *scratch, int64_t *scratch_i64, int32_t deterministic, void *stream)
 {
+    DeviceGuard dev_guard(out);
     if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
         return CMAX_ERR_BAD_SHAPE;
     if (sigma > 0.0f && (!scratch || H < 2 || W < 2)) return CMAX_ERR_WORKSPACE;
@@ -641,6 +664,7 @@ int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_
 int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride, int32_t H,
                      int32_t W, int64_t *out, void *stream)
 {
+    DeviceGuard dev_guard(out);
     if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
         return CMAX_ERR_BAD_SHAPE;
     if (nb > 65535) return CMAX_ERR_UNSUPPORTED;
@@ -675,6 +699,7 @@ int cmax_knn_indices(const float *points, int64_t S, int64_t n, int32_t H, int32
                      int32_t K, int32_t dist_norm, int32_t *ind_out, float *dist_out,
                      void *workspace, size_t workspace_bytes, void *stream)
 {
+    DeviceGuard dev_guard(workspace);
     Geom g;
     int rc = knn_only_geom(H, W, s, S, n, K, &g);
     if (rc != CMAX_OK) return rc;
@@ -700,6 +725,7 @@ int cmax_trajectories_forward(const float *coeff_grid, const float *phi, int64_t
                               int32_t xy_order, int32_t add_offsets, float *trajectories_out,
                               void *stream)
 {
+    DeviceGuard dev_guard(trajectories_out);
     int rc = traj_check(B, S, K, H, W, patch, n_t);
     if (rc) return rc;
     if (!coeff_grid || !phi || !trajectories_out) return CMAX_ERR_BAD_SHAPE;
@@ -717,6 +743,7 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
                                int32_t K, int32_t H, int32_t W, int32_t patch, int32_t n_t,
                                int32_t xy_order, float *dcoeff_grid_out, void *stream)
 {
+    DeviceGuard dev_guard(dcoeff_grid_out);
     int rc = traj_check(B, S, K, H, W, patch, n_t);
     if (rc) return rc;
     if (!dtraj || !phi || !dcoeff_grid_out) return CMAX_ERR_BAD_SHAPE;
@@ -735,6 +762,7 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
 int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, int32_t mode,
                            void *stream)
 {
+    DeviceGuard dev_guard(region);
     if (!region || region_floats < 1024 || region_floats > 0x7fffffff || n_ops < 0)
         return CMAX_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -746,6 +774,10 @@ int cmax_atomic_microbench(float *region, int64_t region_floats, int64_t n_ops, 
         atomic_bench_kernel<1><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
     else if (mode == 2)
         atomic_bench_kernel<2><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
+    else if (mode == 3)
+        atomic_bench_kernel<3><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
+    else if (mode == 4)
+        atomic_bench_kernel<4><<<grid, 256, 0, st>>>(region, (unsigned)region_floats, n_ops);
     else
         return CMAX_ERR_BAD_CONFIG;
     return check_launch();

@@ -97,6 +97,26 @@ int launch_smooth_backward(const Geom &g, const Layout &L, const float *grad_los
 int launch_finalize_losses(const Geom &g, const Layout &L, char *ws, float *losses_out,
                            cudaStream_t st);
 
+// Launches go to the *current* device: make that the device the caller's buffers live on (tensors of
+// a non-current GPU in a single process), restore on exit.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const void *p)
+    {
+        cudaPointerAttributes a;
+        int cur = 0;
+        if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice &&
+            cudaGetDevice(&cur) == cudaSuccess && a.device != cur) {
+            if (cudaSetDevice(a.device) == cudaSuccess) prev = cur;
+        }
+        cudaGetLastError();      // a host pointer / NULL is not an error here
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? CMAX_OK : CMAX_ERR_CUDA; }
 
 // ---- optional per-stage timing (cudaEvent pairs on the launching stream) and launch counter ----

@@ -88,6 +88,7 @@ extern "C" int cmax_dense_flow(const float *traj_flow, const int64_t *pixel_posi
                                int64_t n, int32_t C, int32_t patch, int32_t H, int32_t W,
                                float *patch_flow_out, float *dense_out, void *stream)
 {
+    cmax::DeviceGuard dev_guard(dense_out);
     if (B < 1 || n < 0 || C < 1 || patch < 1 || H < patch || W < patch || !patch_flow_out || !dense_out ||
         (n > 0 && (!traj_flow || !pixel_positions)))
         return CMAX_ERR_BAD_SHAPE;

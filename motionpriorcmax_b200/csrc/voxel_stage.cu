@@ -112,6 +112,7 @@ extern "C" int cmax_voxel_grid(const float *x, const float *y, const float *t, c
                                int64_t n, int32_t C, int32_t H, int32_t W, int32_t norm_type,
                                float *grid_out, double *stats_scratch, void *stream)
 {
+    cmax::DeviceGuard dev_guard(grid_out);
     if (C < 1 || H < 1 || W < 1 || n < 0 || !grid_out || (n > 0 && (!x || !y || !t || !p)))
         return CMAX_ERR_BAD_SHAPE;
     if ((unsigned)norm_type > 2u) return CMAX_ERR_BAD_CONFIG;

@@ -18,6 +18,7 @@ from ..utils import EventImageConverter
 
 class _CmaxLossFunction(torch.autograd.Function):
     """autograd node: forward = cmax_forward, backward = cmax_backward."""
+    strict_events = False        # set per call by FocusLoss.calc (single-threaded caller per process)
 
     @staticmethod
     def forward(ctx, trajectories, times, events, cfg, num_pos_events, want_lut, seg_start=None):
@@ -65,6 +66,17 @@ class _CmaxLossFunction(torch.autograd.Function):
                                   int(num_pos_events), cabi.ptr(iwes), cabi.ptr(losses), cabi.ptr(lut),
                                   cabi.ptr(ws), need, cabi.stream_ptr(dev))
             cabi.check(rc, "cmax_forward")
+        if _CmaxLossFunction.strict_events:
+            # opt-in debug check (synchronises): the kernels skip events whose LUT cell is outside the
+            # table or whose coordinates / bin are not finite and only count them; the reference
+            # raises IndexError / wraps negative indices (focus.py:188) or turns the loss into NaN
+            import ctypes
+            st = (ctypes.c_int64 * 4)()
+            cabi.check(lib.cmax_read_status(cabi.ptr(ws), ctypes.byref(st), cabi.stream_ptr(dev)), "cmax_read_status")
+            if st[0] > 0:
+                raise RuntimeError(f"FocusLoss(strict_events=True): {int(st[0])} valid events were skipped (LUT "
+                                   "cell out of range or non-finite coordinates / bin) - broken loader or a "
+                                   "diverged network")
         ctx.cfg = cfg          # the same config (incl. the backward_follows hint) must reach cmax_backward
         ctx.dims = (B, M, n, int(num_pos_events), need)
         ctx.packed = packed
@@ -116,7 +128,9 @@ class FocusLoss(base.TrajectoryLossBase):
         interpolation_scheme (str): 'mean' or 'iwd'.
         smooth_type (str): 'on_flow_to_tref' or 'on_flow_to_next'.
     Extra (optional, new): deterministic (bool) - int64 fixed-point IWE / LUT-gradient
-        accumulation, run-to-run bit-identical; focus_loss_type ('gradient_magnitude' as upstream
+        accumulation, run-to-run bit-identical; strict_events (bool) - debug check that raises when
+        events had to be skipped (LUT cell out of range, NaN), where upstream raises or returns NaN;
+        focus_loss_type ('gradient_magnitude' as upstream
         calc hard-codes, or 'variance' = upstream utils.calculate_focus_loss(loss_type='variance')).
     """
 
@@ -124,7 +138,7 @@ class FocusLoss(base.TrajectoryLossBase):
                  lut_superpixel_size, focus_loss_norm, dist_norm,
                  scale_iwe_by_dt, mask_image_border, polarity_aware_batching,
                  interpolation_scheme, smooth_type, deterministic=False,
-                 focus_loss_type='gradient_magnitude', **kwargs):
+                 focus_loss_type='gradient_magnitude', strict_events=False, **kwargs):
         super().__init__()
         self.image_shape = tuple(image_shape)
         self.num_tref = num_tref
@@ -141,6 +155,7 @@ class FocusLoss(base.TrajectoryLossBase):
         self.smooth_type = smooth_type
         self.deterministic = bool(deterministic)
         self.focus_loss_type = focus_loss_type      # upstream calc hard-codes 'gradient_magnitude' (focus.py:90)
+        self.strict_events = bool(strict_events)    # debug: raise when the kernels had to skip events
         self.is_needing_offsets = True
         self.imager = EventImageConverter(self.image_shape, deterministic=self.deterministic)
 
@@ -185,6 +200,7 @@ class FocusLoss(base.TrajectoryLossBase):
         events = batch['events']
         if not (trajectories.is_cuda and events.is_cuda):
             raise RuntimeError("FocusLoss (B200) needs CUDA tensors; there is no CPU fallback")
+        _CmaxLossFunction.strict_events = self.strict_events
         # training (a backward will follow): the forward also emits dL/dIWE from its image pass
         cfg = self._cfg_train if (trajectories.requires_grad and torch.is_grad_enabled()) else self._cfg
         if hasattr(events, 'fine_start'):

@@ -29,6 +29,12 @@ class EventImageConverter(object):
     # -- upstream :45-74 ------------------------------------------------------
     def create_iwe(self, events: torch.Tensor, method: str = "bilinear_vote", sigma: int = 1,
                    weight=1.0) -> torch.Tensor:
+        if hasattr(events, "fine_start") or hasattr(events, "seg_start"):
+            # loader-side layouts (io.CompactEvents / io.PackedEvents) as `batch['events']`: what the
+            # image-logging callback hands over (upstream src/utils/logging.py:76-79).  Rendered from
+            # the valid events; the reference's padding rows (all zero) each add one vote at pixel
+            # (0, 0) there, which this rendering does not reproduce.
+            events, weight = self._rows_of_packed(events, weight)
         if not isinstance(events, torch.Tensor):
             e = f"Non-supported type of events. {type(events)}"
             raise RuntimeError(e)
@@ -68,11 +74,32 @@ class EventImageConverter(object):
         nb, m, c = ev.shape
         out = torch.empty((nb, h, w), dtype=torch.int64, device=ev.device)
         lib = cabi.load()
-        cabi.check(lib.cmax_count_image(cabi.ptr(ev), nb, m, c, h, w, cabi.ptr(out),
-                                        cabi.stream_ptr(ev.device)), "cmax_count_image")
+        with torch.cuda.device(ev.device):
+            cabi.check(lib.cmax_count_image(cabi.ptr(ev), nb, m, c, h, w, cabi.ptr(out),
+                                            cabi.stream_ptr(ev.device)), "cmax_count_image")
         return out.squeeze()
 
     # ------------------------------------------------------------------------
+    @staticmethod
+    def _rows_of_packed(events, weight):
+        """(rows [B, M, >=2], weight [B, M]) of a loader-side layout: records / coordinates of the
+        valid events, a 0 weight on the unused tail of every window."""
+        if not isinstance(weight, (int, float)) or float(weight) != 1.0:
+            raise NotImplementedError("per-event weights with a packed / compact events layout")
+        if hasattr(events, "fine_start"):                    # CompactEvents: ragged [T, 3]
+            counts = events.fine_start[:, -1].to(torch.int64)
+            off = events.sample_off.to(torch.int64)
+            B, Mp = counts.shape[0], int(events.max_count)
+            idx = off[:-1, None] + torch.arange(Mp, device=counts.device)[None]
+            mask = torch.arange(Mp, device=counts.device)[None] < counts[:, None]
+            rows = events.coords[idx.clamp_(max=events.coords.shape[0] - 1)]
+        else:                                                # PackedEvents: [B, M, 4]
+            counts = events.seg_start[:, -1].to(torch.int64)
+            rows = events.records
+            mask = torch.arange(rows.shape[1], device=rows.device)[None] < counts[:, None]
+        rows = torch.where(mask[..., None], rows, torch.zeros((), dtype=rows.dtype, device=rows.device))
+        return rows, mask.to(torch.float32)
+
     @staticmethod
     def _prep(events: torch.Tensor) -> torch.Tensor:
         if not events.is_cuda:
@@ -81,6 +108,13 @@ class EventImageConverter(object):
             events = events[None]
         if events.dim() != 3 or events.shape[-1] < 2:
             raise ValueError("events must be [(b,) n_events, >=2]")
+        if events.requires_grad and torch.is_grad_enabled():
+            # upstream create_iwe is differentiable in the coordinates; this stand-alone entry is a
+            # forward-only renderer (the loss path has its own backward) - refuse instead of silently
+            # cutting the graph
+            raise RuntimeError("EventImageConverter (B200) is forward only: events require grad. Use "
+                               "FocusLoss.calc for a differentiable IWE, or call under torch.no_grad() / "
+                               "with events.detach().")
         return events.detach().to(torch.float32).contiguous()
 
     def _vote(self, events: torch.Tensor, weight, sigma: float) -> torch.Tensor:
@@ -90,6 +124,8 @@ class EventImageConverter(object):
         wt = None
         if isinstance(weight, torch.Tensor):
             assert weight.shape == events.shape[:-1]
+            if weight.requires_grad and torch.is_grad_enabled():
+                raise RuntimeError("EventImageConverter (B200) is forward only: weight requires grad")
             wt = weight.detach().to(torch.float32).reshape(nb, m).contiguous()
         elif float(weight) != 1.0:
             wt = torch.full((nb, m), float(weight), dtype=torch.float32, device=ev.device)
@@ -98,9 +134,10 @@ class EventImageConverter(object):
         scratch64 = (torch.empty((nb, h, w), dtype=torch.int64, device=ev.device)
                      if self.deterministic else None)
         lib = cabi.load()
-        rc = lib.cmax_create_iwe(cabi.ptr(ev), cabi.ptr(wt), nb, m, c, h, w, sigma, cabi.ptr(out),
-                                 cabi.ptr(scratch), cabi.ptr(scratch64), int(self.deterministic),
-                                 cabi.stream_ptr(ev.device))
+        with torch.cuda.device(ev.device):
+            rc = lib.cmax_create_iwe(cabi.ptr(ev), cabi.ptr(wt), nb, m, c, h, w, sigma, cabi.ptr(out),
+                                     cabi.ptr(scratch), cabi.ptr(scratch64), int(self.deterministic),
+                                     cabi.stream_ptr(ev.device))
         cabi.check(rc, "cmax_create_iwe")
         if sigma > 0:
             out = out[:, None]            # upstream blurs a [nb, 1, H, W] view, then squeezes

@@ -13,7 +13,8 @@ n_ops = 1 << 28
 for name, floats in (("iwe_plane_1.2MB", 480 * 640), ("batch14_pab_34MB", 14 * 2 * 480 * 640),
                      ("larger_than_L2_512MB", 128 * 1024 * 1024)):
     region = torch.zeros(floats, dtype=torch.float32, device=dev)
-    for mode, mname in ((0, "red_global_f32"), (1, "atom_shared_f32"), (2, "atom_global_u64")):
+    for mode, mname in ((0, "red_global_f32"), (1, "atom_shared_f32"), (2, "atom_global_u64"),
+                        (3, "red_global_v2_f32"), (4, "red_global_v4_f32")):
         if mode == 2 and floats % 2:
             continue
         for _ in range(2):
@@ -27,4 +28,6 @@ for name, floats in (("iwe_plane_1.2MB", 480 * 640), ("batch14_pab_34MB", 14 * 2
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         out[f"{mname}/{name}"] = {"ops": n_ops, "ms": ms, "Gops_per_s": n_ops / ms / 1e6}
+        if mode >= 3:            # n_ops scalar votes travel in n_ops / 2 vector requests
+            out[f"{mname}/{name}"]["Grequests_per_s"] = n_ops / 2 / ms / 1e6
 print(json.dumps(out, indent=1))

@@ -407,6 +407,64 @@ def test_error_behaviour_mirrors_reference():
                                                                 "num_pos_events": 5})
 
 
+def test_api_corner_behaviour():
+    """strict_events raises on skipped events; the stand-alone imager refuses to cut a graph silently
+    and renders the loader-side layouts (what DsecImageLoggingCallback passes, logging.py:76-79);
+    a negative smoothness weight with on_flow_to_next is rejected (the reference crashes on it)."""
+    from motionpriorcmax_b200 import cabi, io, synthetic
+    from motionpriorcmax_b200.losses import LossFactory
+    dev = _cuda()
+    cfg = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(48, 64), num_knn=6, num_bins=5)
+    traj, times, ev, npos, _ = _synthetic_case(cfg, 2, [3000, 2000], 1, seed=9)
+    bad = ev.copy()
+    bad[0, :7, 0] = -9.0                                     # LUT row -3: outside the table
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, strict_events=True))
+    t = torch.as_tensor(traj, device=dev)
+    tm = torch.as_tensor(times, device=dev)
+    L.calc(t, tm, {"events": torch.as_tensor(ev, device=dev), "num_pos_events": npos})      # clean: fine
+    with pytest.raises(RuntimeError, match="7 valid events were skipped"):
+        L.calc(t, tm, {"events": torch.as_tensor(bad, device=dev), "num_pos_events": npos})
+    # imager: forward only
+    e = torch.as_tensor(ev, device=dev).clone().requires_grad_()
+    with pytest.raises(RuntimeError, match="forward only"):
+        L.imager.create_iwe(e)
+    with torch.no_grad():
+        L.imager.create_iwe(e)
+    # imager on the loader-side layouts == imager on the valid rows of the reference layout
+    evt = torch.as_tensor(ev)
+    valid_rows = evt.clone()
+    wt = evt[..., 5].to(dev)
+    ref = L.imager.create_iwe(valid_rows.to(dev), sigma=1, weight=wt)
+    for packed in (io.pack_events_native(evt, npos, L).to(dev), io.pack_events_compact(evt, npos, L).to(dev)):
+        got = L.imager.create_iwe(packed, method="bilinear_vote", sigma=1)
+        assert got.shape == ref.shape and rel_err(got.cpu().numpy(), ref.cpu().numpy()) < TOL
+    # reference crash -> error code
+    neg = cabi.make_config(**{k: v for k, v in dict(cfg, smooth_type="on_flow_to_next", smooth_weight=-0.1).items()})
+    assert cabi.load().cmax_workspace_bytes(neg, 1, 100, 192) == 0
+
+
+def test_learned_basis_table_gets_a_gradient():
+    """trajectories_from_table (the route for the reference's learned MLP basis, basis.py:26-27)
+    back-propagates into the basis table as the reference back-propagates into basis_network(t)."""
+    from motionpriorcmax_b200 import synthetic, trajectories as tj
+    dev = _cuda()
+    H, W, K, nt = 32, 48, 3, 7
+    cg = synthetic.make_coeff_grid(2, K, H, W, sigma_px=4.0, seed=5, coarse=(3, 4)).to(dev).requires_grad_()
+    phi = torch.randn(nt, K, device=dev, requires_grad=True)
+    out = tj.trajectories_from_table(cg, phi, 4, add_offsets=True)
+    wgt = torch.randn_like(out)
+    (out * wgt).sum().backward()
+    # plain torch restatement: traj[b,t,j,a] = sum_k phi[t,k] c_a[b,k,j] + pixel
+    cgr = cg.detach().clone().requires_grad_()
+    phir = phi.detach().clone().requires_grad_()
+    tile = cgr[:, 0, :, 2::4, 2::4].reshape(2, 2 * K, -1)
+    ref = torch.stack((torch.einsum("tk,bkj->btj", phir, tile[:, :K]),
+                       torch.einsum("tk,bkj->btj", phir, tile[:, K:])), -1)
+    (ref * wgt).sum().backward()
+    assert rel_err(phi.grad.cpu().numpy(), phir.grad.cpu().numpy()) < TOL
+    assert rel_err(cg.grad.cpu().numpy(), cgr.grad.cpu().numpy()) < TOL
+
+
 def test_front_end_matches_oracle_and_golden():
     from motionpriorcmax_b200 import trajectories as tj
     from oracle import focus_oracle as fo
