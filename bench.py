@@ -154,9 +154,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (oracle port)
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=1):
+def cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=1, split=False):
     """One loss forward+backward of the CPU oracle on the first `sample_windows` windows.
-    Returns (seconds, valid events processed)."""
+    Returns (seconds, valid events processed[, seconds of the LUT stage's K-NN search alone])."""
     from oracle import focus_oracle as fo
     B = min(sample_windows, ev.shape[0])
     evs = ev[:B].numpy()
@@ -169,7 +169,14 @@ def cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=1):
     fo.trajectories_backward(g["dtraj"], times, 4, w["K"], w["basis"], tuple(cg[:B].shape),
                              dtype=np.float32)
     dt = time.perf_counter() - t0
-    return dt, int(evs[..., 5].sum())
+    if not split:
+        return dt, int(evs[..., 5].sum())
+    # the fixed LUT-stage cost (exhaustive K-NN of interpolate_flow, focus.py:115-180) on its own:
+    # timed on one window and scaled (the exhaustive search is exactly linear in the windows)
+    grid, _, _ = fo.lut_grid(cfg["image_shape"], cfg["lut_superpixel_size"])
+    t1 = time.perf_counter()
+    fo.knn_bruteforce(np.asarray(traj, np.float32)[:1, cfg["num_tref"]:], grid, cfg["num_knn"], cfg["dist_norm"], True)
+    return dt, int(evs[..., 5].sum()), (time.perf_counter() - t1) * B
 
 
 def run_reference(args):
@@ -177,26 +184,29 @@ def run_reference(args):
     if rank != 0:
         return
     cfg, w = workload(args.variant, args.batch, args.events)
-    cg, ev, npos, _ = make_inputs(cfg, dict(w, B=1), 0)         # bounded sample: one window
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_step(cfg, w, cg, ev, npos)
-    secs, n_ev = [], 0
-    steps = max(1, min(args.steps, 3))
+    cg, ev, npos, _ = make_inputs(cfg, w, 0)                    # the same batch rank 0 of our arm gets
+    B = ev.shape[0]
+    warm = max(0, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 2))                          # ~35 s per 14-window step on 16 cores
+    if warm:
+        cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=1)
+    secs, n_ev, knn_s = [], 0, 0.0
     for _ in range(steps):
-        dt, n_ev = cpu_reference_step(cfg, w, cg, ev, npos)
+        dt, n_ev, knn_s = cpu_reference_step(cfg, w, cg, ev, npos, sample_windows=B, split=True)
         secs.append(dt)
     t = statistics.median(secs)
     val = n_ev / t
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "cmax_loss_fwd_bwd_events_per_sec", "value": val,
-        "unit": "events/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "unit": "events/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "sample": "1 window of the batch per step",
+        "config": {"workload": w["name"], "per_rank_batch": B, "sample": "the full batch of rank 0 per step",
                    "events_per_step": n_ev},
         "cpu_baseline": {"value": val, "unit": "events/s", "cores": cores, "kind": "port",
-                         "sample": f"1 window ({n_ev} events) fwd+bwd, oracle port of the reference "
+                         "lut_stage_knn_s": knn_s, "event_and_image_stage_s": max(t - knn_s, 0.0),
+                         "sample": f"{B} windows ({n_ev} events) fwd+bwd per step, oracle port of the reference "
                                    f"loss (numpy event stage 1 thread + C/OpenMP exhaustive KNN on "
                                    f"{cores} threads); the Python+pykeops reference cannot run on the box"},
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -534,18 +544,23 @@ def run_ours(args):
         except Exception:
             pass
         stage_kernels = {
-            "knn_select": "knn_fast_kernel x num_bins (per-bin launches) + knn_heap_kernel [+ lut_accumulate_kernel]",
-            "lut_backward": "lut_backward_kernel + lut_backward_assemble_kernel",
+            "knn_select": "knn_fast_kernel x num_bins (per-bin launches) + knn_warp_kernel + knn_heap_kernel "
+                          "[+ lut_accumulate_kernel]",
+            "lut_backward": "lut_backward_tile_kernel + lut_backward_assemble_kernel",
             "event_forward": "event_forward_kernel", "event_backward": "event_backward_kernel"}
         # the event kernels are the HBM/atomic-bound ones: report them against both ceilings
+        # atomic side of the roofline: the L2 atomic unit retires ~192 G REQUESTS/s whatever their
+        # width (scalar, v2, v4 all measured: profiles/r02_atomic_microbench.json), so the bound
+        # counts requests: forward 2 per valid event when both corner pairs go out as one vector red
+        # each (2.5 measured: unaligned pairs split), backward 1 (the (g_y, g_x) pair)
         r_atomic = None
         try:
-            mb = json.load(open(os.path.join(ROOT, "profiles", "r01_atomic_microbench.json")))
-            r_atomic = mb["red_global_f32/batch14_pab_34MB"]["Gops_per_s"]
+            mb = json.load(open(os.path.join(ROOT, "profiles", "r02_atomic_microbench.json")))
+            r_atomic = mb["red_global_v2_f32/batch14_pab_34MB"]["Grequests_per_s"]
         except Exception:
             pass
         ev_roof = {}
-        for k, reqs_per_event in (("event_forward", 3.0), ("event_backward", 1.0)):
+        for k, reqs_per_event in (("event_forward", 2.5), ("event_backward", 1.0)):
             if k in per_launch:
                 t = per_launch[k] * 1e-3
                 ev_roof[k] = {"ms": per_launch[k], "hbm_GBps": stage_bytes[k] / t / 1e9,
@@ -572,7 +587,17 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "whole_step": {"algorithmic_bytes": total_bytes,
                                         "achieved": total_bytes / (ms_step * 1e-3) / 1e9,
-                                        "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                                        "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                                        "hbm_bound_ms": total_bytes / peak / 1e6,
+                                        "atomic_requests": 3.0 * n_valid,
+                                        "atomic_bound_ms": (3.0 * n_valid / r_atomic / 1e6) if r_atomic else None,
+                                        "combined_bound_ms": max(total_bytes / peak / 1e6,
+                                                                 (3.0 * n_valid / r_atomic / 1e6) if r_atomic else 0.0),
+                                        "frac_of_combined_bound": max(total_bytes / peak / 1e6,
+                                                                      (3.0 * n_valid / r_atomic / 1e6) if r_atomic else 0.0)
+                                        / ms_step,
+                                        "note": "combined = max(HBM time of the algorithmic bytes, L2-atomic time of "
+                                                "3 vector-red requests per valid event at the measured request rate)"},
                          "event_kernels": ev_roof,
                          "note": "the dominant stage is the exact K-NN LUT build: a fixed per-window "
                                  "cost that is instruction/latency bound, not HBM bound",
@@ -628,12 +653,13 @@ def run_ours(args):
                 "value_rank0_with_device_pack_each_step": n_valid / ((ms_p + packed["ms_pack"]) * 1e-3),
                 "stage_ms_per_launch": packed["stage"]}
         if world == 1 and not args.no_cpu:
-            dt, n_ev = cpu_reference_step(cfg, w, cg_h, ev_h, npos)
+            dt, n_ev, knn_s = cpu_reference_step(cfg, w, cg_h, ev_h, npos, split=True)
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = {
                 "value": n_ev / dt, "unit": "events/s", "cores": cores, "kind": "port",
+                "lut_stage_knn_s": knn_s, "event_and_image_stage_s": max(dt - knn_s, 0.0),
                 "sample": f"1 window ({n_ev} events) fwd+bwd in {dt:.2f} s: numpy event stage "
-                          f"(1 thread) + C/OpenMP exhaustive KNN ({cores} threads)"}
+                          f"(1 thread) + C/OpenMP exhaustive KNN ({cores} threads, {knn_s:.2f} s of it)"}
         emit(line)
     if dist is not None:
         try:
