@@ -37,7 +37,6 @@ struct Geom {                 // derived sizes, passed by value to kernels
     int r_fast;               // window radius of the staged fast path
     int l1dist, l2focus, scale_dt, mask_border, pab, iwd, smooth_next, det, variance;
     int fuse_image;           // training hint: the forward also produces dL/dIWE (image stage fused)
-    int dbg;                  // experiment switches (CMAX_FWD_OPT), 0 in production
     float smooth_w;
     int64_t B, M, n, S;       // S = B * nb
     int64_t npos;

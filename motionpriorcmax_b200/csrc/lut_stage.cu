@@ -275,7 +275,7 @@ __device__ __forceinline__ Query make_query(int c, const Geom &g)
 // ---------------------------------------------------------------------------------------------
 // 2. fast path
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 960;     // staged records per CTA (points + 3 sentinels per window row)
+constexpr int kStageCap = 1152;    // staged records per CTA (points + 3 sentinels per window row)
 constexpr int kListCap = 24;       // boundary candidates kept per thread
 constexpr int kRowPad = 3;         // sentinel records after every staged window row
 constexpr int kWinRows = kKnnTileH + 2 * 10;
@@ -370,10 +370,10 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
 {
     typedef float4 Rec;                                 // (y, x, flow_y, flow_x)
     __shared__ __align__(16) Rec s_pt[kStageCap];
-    __shared__ int s_pj[kStageCap];
+    __shared__ int s_rowga[kWinRows];                   // first record of every staged row in HBM
     __shared__ __align__(8) unsigned long long s_bar;   // completion of the bulk copies
     __shared__ unsigned short s_cell[kWinRows][kWinCols + 1];     // local run starts (< kStageCap)
-    // boundary candidates: only the staged index is kept (u16, + the slice id in bits 10..13);
+    // boundary candidates: only the staged index is kept (u16, + the slice id in bits 11..14);
     // distances are recomputed from the staged point on demand
     __shared__ unsigned short s_li[kListCap][kKnnBlock];
     __shared__ int s_rowbase[kWinRows + 1];
@@ -461,11 +461,9 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
             const int base = s_rowbase[lr], len = s_rowbase[lr + 1] - base - kRowPad;
             for (int lc = lane; lc <= ncol; lc += 32)
                 s_cell[lr][lc] = (unsigned short)min(__ldg(crow + lc) - ga + base, kStageCap);
-            for (int k = lane; k < len; k += 32) s_pj[base + k] = __ldg(sorted_j + ga + k);
-            if (lane < kRowPad) {                          // sentinels: infinitely far, never listed
+            if (lane == 0) s_rowga[lr] = ga;
+            if (lane < kRowPad)                            // sentinels: infinitely far, never listed
                 s_pt[base + len + lane] = make_float4(1e30f, 1e30f, 0.0f, 0.0f);
-                s_pj[base + len + lane] = 0x7fffffff;
-            }
         }
         mbar_wait(&s_bar, 0);
     }
@@ -494,7 +492,7 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
             const float dy = __fsub_rn(qy, pt.x), dx = __fsub_rn(qx, pt.y);
             return L1D ? __fadd_rn(fabsf(dy), fabsf(dx)) : __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
         };
-        auto list_d = [&](int u) { return dist_at(s_li[u][tid] & 0x3ff); };   // recomputed on demand
+        auto list_d = [&](int u) { return dist_at(s_li[u][tid] & 0x7ff); };   // recomputed on demand
         // Columns of window row `lr` that can hold a point with d < hi: the row's cells are clipped
         // to the disc (l1: diamond) of that radius around the query - about half of the square
         // window.  Conservative by 1e-5 relative, like window_bound: cells are assigned with a
@@ -577,12 +575,12 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                 if (overflow) m = kListCap + 1;
                 // slice the listed candidates (kept out of the hot loop: nearly every warp
                 // iteration has *some* lane inside the bracket)
-                for (int u = 0; u < min(m, kListCap); ++u) {
+                for (int u = 0; u < (m <= kListCap ? m : 0); ++u) {        // (a full list holds unwritten slots)
                     const int bk = bucket_of(list_d(u), lo, invw);         // 1..8
                     const unsigned inc = 1u << ((bk & 3) << 3);
                     hlo += bk < 4 ? inc : 0u;
                     hhi += (bk >= 4 && bk < 8) ? inc : 0u;
-                    s_li[u][tid] |= (unsigned short)(bk << 10);
+                    s_li[u][tid] |= (unsigned short)(bk << 11);
                 }
                 // slice of the bracket that holds the K-th key
                 int bstar = -1, cum = below;
@@ -597,7 +595,7 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
                     int mm = 0;
                     for (int u = 0; u < m; ++u) {
                         const int pk = s_li[u][tid];
-                        const int bk = pk >> 10, i = pk & 0x3ff;
+                        const int bk = pk >> 11, i = pk & 0x7ff;
                         if (bk < bstar) {
                             if (FUSED) {
                                 const float2 f = rec_flow(s_pt[i]);
@@ -712,18 +710,26 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
         }
         if (resolved) {
             // order the first `need` boundary candidates by (d, trajectory index)
+            // (the trajectory index is only needed to break exact distance ties and for the final
+            // key: it is read from HBM on demand instead of being staged for every record)
+            auto jof = [&](int idx) {
+                int lr = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1)
+                    if (lr + st < nrow && s_rowbase[lr + st] <= idx) lr += st;
+                return __ldg(sorted_j + s_rowga[lr] + (idx - s_rowbase[lr]));
+            };
             for (int t = 0; t < need; ++t) {
                 int best = t;
                 float bd = list_d(t);
-                int bj = s_pj[s_li[t][tid]];
                 for (int u = t + 1; u < m; ++u) {
                     const float du = list_d(u);
-                    if (du < bd || (du == bd && s_pj[s_li[u][tid]] < bj)) {
+                    if (du < bd || (du == bd && jof(s_li[u][tid]) < jof(s_li[best][tid]))) {
                         best = u;
                         bd = du;
-                        bj = s_pj[s_li[u][tid]];
                     }
                 }
+                const int bj = t == need - 1 ? jof(s_li[best][tid]) : 0;
                 const int ib = s_li[best][tid];
                 if (best != t) {
                     s_li[best][tid] = s_li[t][tid];
@@ -1258,7 +1264,8 @@ lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *_
 // exceeds the staging capacity take gather_generic, the global-memory walk of the same lattice.
 // Stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
 // fixed order -> deterministic.
-constexpr int kBwdTileW = 16;                     // cell-list cells per CTA: TH x 16
+constexpr int kBwdTileH = 8, kBwdTileW = 16;      // cell-list cells per CTA (measured: 16x16 / 288 threads
+constexpr int kBwdBlock = 128;                    // and 160 / 192 threads per 8x16 tile are all slower)
 constexpr int kBwdWinCap = 1280;                  // staged LUT cells per CTA (incl. row padding)
 constexpr int kBwdMaxRows = 64;
 
@@ -1375,8 +1382,8 @@ __device__ __noinline__ void gather_generic(const LatticeGeom g, int slab, int b
 
 // RT = compile-time R (1, 3, 5, 10) or 0 = runtime R; TH = cell rows per tile, NT = threads per CTA
 template <bool L1D, bool IWD, bool F2N, int RT, int TH, int NT>
-__global__ void __launch_bounds__(NT, TH == 8 ? (NT == 128 ? 8 : (NT == 160 ? 6 : 5)) : 3)
-lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, int refine, const int *__restrict__ cell_start,
+__global__ void __launch_bounds__(NT, 8)
+lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, const int *__restrict__ cell_start,
                          const float4 *__restrict__ sorted_all, const float *__restrict__ tau,
                          const int *__restrict__ jcut, const float *__restrict__ wsum,
                          const unsigned *__restrict__ tau_max, const unsigned *__restrict__ tile_max,
@@ -1386,8 +1393,7 @@ lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, int refine, con
     __shared__ float2 s_key[kBwdWinCap];                    // (tau, jcut bits) of the staged LUT cells
     __shared__ float2 s_dl[RT == 1 ? kBwdWinCap : 1];       // dLUT (single reference time)
     __shared__ float2 s_dn[F2N ? kBwdWinCap : 1];           // d flow_to_next
-    __shared__ float s_rowmax[kBwdMaxRows], s_rowmax2[kBwdMaxRows];
-    constexpr int kBwdTileH = TH, kBwdBlock = NT;
+    __shared__ float s_rowmax2[kBwdMaxRows];
     __shared__ int s_run[kBwdTileH + 1], s_runbase[kBwdTileH];
     __shared__ float s_tbest;
 
@@ -1475,8 +1481,8 @@ lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, int refine, con
     const float2 *dn_s = F2N ? reinterpret_cast<const float2 *>(df2n) + ((int64_t)b * (g.nb - 1) + bin) * g.q
                              : nullptr;
     const bool do_next = F2N && bin < g.nb - 1;
-    float rho = rho0;
-    int jyA = iyA, jyB = iyB, jxA = ixA, jxB = ixB;          // refined window (inside the staged one)
+    const float rho = rho0;
+    const int jyA = iyA, jyB = iyB, jxA = ixA, jxB = ixB;
     if (fast) {
         for (int lr = tid >> 5; lr < nrows; lr += kBwdBlock / 32) {     // one warp per lattice row
             const int o = (iyA + lr) * Wq + ixA;
@@ -1491,37 +1497,14 @@ lut_backward_tile_kernel(const float *__restrict__ traj, Geom g, int refine, con
             }
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o2));
-            if (lane == 0) s_rowmax[lr] = rm;
-        }
-        __syncthreads();
-        // The tile-level reach comes from whole 16x8-query tiles; the staged keys give a tighter
-        // one: the maximum over the window bounds the reach, which shrinks the window, whose row
-        // maxima (over its own columns only) bound every row of the walk.
-        float m1 = -1.0f;
-        if (!refine) m1 = tbest;
-        for (int lr = lane; lr < nrows; lr += 32) m1 = fmaxf(m1, s_rowmax[lr]);
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o2));
-        const float rho1 = fminf(reach_of(m1), rho0);
-        jyA = max(iyA, lat_lo(Y0 - rho1, g.Hq - 1));
-        jyB = min(iyB, lat_hi(Y1 + rho1, g.Hq - 1));
-        jxA = max(ixA, lat_lo(X0 - rho1, Wq - 1));
-        jxB = min(ixB, lat_hi(X1 + rho1, Wq - 1));
-        for (int lr = (tid >> 5) + (jyA - iyA); lr <= jyB - iyA; lr += kBwdBlock / 32) {
-            float rm = -1.0f;
-            for (int c = jxA - ixA + lane; c <= jxB - ixA; c += 32) rm = fmaxf(rm, s_key[lr * ncp + c].x);
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o2));
-            // scaled once here: `rem` of the row walk is rowmax * 1.0001 + 1e-3 - dy2
+            // the row's largest tau bounds the columns of that row a point can be a neighbour of
+            // (scaled once here: `rem` of the row walk is rowmax * 1.0001 + 1e-3 - dy2).  Tightening
+            // the window further with the staged maxima (reach -> smaller window -> row maxima over
+            // its columns only) was measured: same candidate count, 6 % more instructions.
             if (lane == 0) s_rowmax2[lr] = rm < 0.0f ? -1.0f : rm * 1.0001f + 1e-3f;
         }
-        __syncthreads();
-        float m2 = -1.0f;
-        for (int lr = jyA - iyA + lane; lr <= jyB - iyA; lr += 32) m2 = fmaxf(m2, s_rowmax2[lr]);
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o2));
-        rho = fminf(reach_of(m2), rho1);
     }
+    __syncthreads();
 
     const float invK = 1.0f / (float)g.K;
     const int stride = R + (F2N ? 1 : 0);
@@ -1698,10 +1681,7 @@ static void launch_fast(const Geom &g, int bin, int chain_len, dim3 grid, cudaSt
 int launch_lut_forward(const Geom &g_in, const Layout &L, const float *traj, char *ws,
                        float *flow_lut_out, int32_t *ind_out, float *dist_out, cudaStream_t st)
 {
-    static int fwd_opt = -1;                // experiment switch: bit 0 = no in-kernel second chance
-    if (fwd_opt < 0) { const char *e = getenv("CMAX_FWD_OPT"); fwd_opt = e ? atoi(e) : 0; }
-    Geom g = g_in;
-    g.dbg = fwd_opt;
+    const Geom &g = g_in;
     int *cell_start = reinterpret_cast<int *>(ws + L.cell_start);
     float4 *sorted = reinterpret_cast<float4 *>(ws + L.sorted);
     float4 *recs = reinterpret_cast<float4 *>(ws + L.recs);
@@ -1836,31 +1816,14 @@ struct BwdArgs {
     const unsigned *tmax, *tile_max;
     const float *dlut, *df2n;
     float2 *part;
-    int big_tile, refine, nthr;
 };
 
 template <bool L1D, bool IWD, bool F2N>
 static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const BwdArgs &a)
 {
-#define BWD_LAUNCH(RT_)                                                                                         \
-    do {                                                                                                         \
-        if (a.big_tile)                                                                                          \
-            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 16, 288><<<grid, 288, 0, st>>>(                      \
-                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
-                a.df2n, a.part);                                                                                 \
-        else if (a.nthr == 192)                                                                                  \
-            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 192><<<grid, 192, 0, st>>>(                       \
-                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
-                a.df2n, a.part);                                                                                 \
-        else if (a.nthr == 160)                                                                                  \
-            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 160><<<grid, 160, 0, st>>>(                       \
-                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
-                a.df2n, a.part);                                                                                 \
-        else                                                                                                     \
-            lut_backward_tile_kernel<L1D, IWD, F2N, RT_, 8, 128><<<grid, 128, 0, st>>>(                       \
-                a.traj, g, a.refine, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, \
-                a.df2n, a.part);                                                                                 \
-    } while (0)
+#define BWD_LAUNCH(RT_)                                                                                     \
+    lut_backward_tile_kernel<L1D, IWD, F2N, RT_, kBwdTileH, kBwdBlock><<<grid, kBwdBlock, 0, st>>>(          \
+        a.traj, g, a.cell_start, a.sorted, a.tau, a.jcut, a.wsum, a.tmax, a.tile_max, a.dlut, a.df2n, a.part)
     if (g.R == 1) BWD_LAUNCH(1);
     else if (!F2N && g.R == 3) BWD_LAUNCH(F2N ? 0 : 3);        // compile-time R keeps the per-reference
     else if (!F2N && g.R == 5) BWD_LAUNCH(F2N ? 0 : 5);        // accumulators in registers (on_flow_to_next
@@ -1872,10 +1835,7 @@ static void launch_bwd(const Geom &g, dim3 grid, cudaStream_t st, const BwdArgs 
 int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char *ws,
                         float *dtraj, cudaStream_t st)
 {
-    static int opt = -1;                    // experiment switch: bit 0 = 16x16-cell tiles, bit 1 = no refinement
-    if (opt < 0) { const char *e = getenv("CMAX_BWD_OPT"); opt = e ? atoi(e) : 0; }
-    const int th = (opt & 1) ? 16 : 8;
-    const unsigned ctiles = (unsigned)(((g.Hc + th - 1) / th) * ((g.Wc + kBwdTileW - 1) / kBwdTileW));
+    const unsigned ctiles = (unsigned)(((g.Hc + kBwdTileH - 1) / kBwdTileH) * ((g.Wc + kBwdTileW - 1) / kBwdTileW));
     dim3 grid(ctiles, (unsigned)g.nb, (unsigned)g.B);
     const bool want_next = g.smooth_next && g.smooth_w > 0.0f && g.nb > 1;
     float2 *dtraj_part = reinterpret_cast<float2 *>(ws + L.bpart);
@@ -1891,9 +1851,6 @@ int launch_lut_backward(const Geom &g, const Layout &L, const float *traj, char 
     a.dlut = reinterpret_cast<const float *>(ws + L.dlut);
     a.df2n = reinterpret_cast<const float *>(ws + L.df2n);
     a.part = dtraj_part;
-    a.big_tile = opt & 1;
-    a.refine = (opt & 2) ? 0 : 1;
-    a.nthr = (opt & 4) ? 192 : ((opt & 8) ? 160 : 128);
     StageScope sc(ST_LUT_BWD, st);
     count_launch(2);
     const int key = (g.l1dist ? 4 : 0) | (g.iwd ? 2 : 0) | (want_next ? 1 : 0);

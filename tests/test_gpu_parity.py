@@ -767,6 +767,36 @@ def test_full_size_batch_takes_the_per_bin_chain_and_matches_oracle(dist):
     _assert_grad_close(r["dtraj"], g["dtraj"], cfg, traj, times, ev, npos, gpu_iwes=r["iwes"])
 
 
+def test_bench_configuration_runs_clean_and_reproducibly():
+    """The exact rank-0 batch of bench.py (14 windows, log-normal event counts, 480x640): the
+    K-NN chain at its real size (boundary lists that fill up, staged windows beyond 1024 records,
+    work-list kernels) must run without a launch error, settle every LUT cell, and - in
+    deterministic mode - reproduce itself bit for bit."""
+    import bench
+    from motionpriorcmax_b200 import cabi, trajectories as tj
+    from motionpriorcmax_b200.losses import LossFactory
+    dev = _cuda()
+    cfg, w = bench.workload("dsec", None, 400_000)              # 14 windows x 0.4 M events: quick on the host side
+    w["lognormal"] = True
+    cg, ev, npos, n_valid = bench.make_inputs(cfg, w, 0)
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=True))
+    times = L.get_reconstruction_times(dev)
+    times[0] = 0.5
+    evd = ev.to(dev)
+    outs = []
+    for _ in range(2):
+        c = cg.to(dev).requires_grad_()
+        loss, _, misc = L.calc(tj.calculate_trajectories_at_t(c, times, 4, 1, "polynomial"), times,
+                               {"events": evd, "num_pos_events": npos}, return_flow_lut=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss) and torch.isfinite(misc["flow_lut"]).all() and torch.isfinite(c.grad).all()
+        outs.append((loss.item(), misc["flow_lut"].clone(), c.grad.clone()))
+    miss = cabi.worklist_reasons(cabi.stream_ptr(dev))
+    assert miss["heap_fallback"] <= miss["total"] < 0.01 * 14 * 15 * 19200, miss
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 @pytest.mark.parametrize("B", [6, 9])
 def test_per_bin_chain_batches_match_oracle(B):
     """Batches of >= 6 windows take the per-bin launch chain of the K-NN stage (previous-bin
