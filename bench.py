@@ -2,7 +2,7 @@
 """bench.py - CMax loss forward+backward throughput (events/s) on B200, per BASELINE.json.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--events M] [--batch B] [--variant dsec|dsec_tref5|evimo2|k3_det]
+                    [--events M] [--batch B] [--variant dsec|dsec_tref5|evimo2|evimo2_tref10|k3_det]
 
 One "step" = one pass of the loss hot path over one batch of synthetic event windows:
 coeff_grid -> trajectories (fused front end) -> FocusLoss.calc -> backward to d coeff_grid.
@@ -60,6 +60,12 @@ def workload(variant: str, batch: int | None, events: int | None):
     elif variant == "evimo2":
         cfg = dict(synthetic.EVIMO2_LOSS_CONFIG)
         w = dict(name="evimo2_300ms_b6_384x512_bezier10", B=batch or 6, K=10, basis="bezier",
+                 median=events or 1_000_000, lognormal=False, deterministic=False, integer=True)
+    elif variant == "evimo2_tref10":
+        # the "10 reference times" variant of the EVIMO2 configuration (BASELINE.json configs[2];
+        # experiment yaml :21-35 with the only multi-reference combination focus.py:49-51 allows)
+        cfg = synthetic.multi_tref_variant(synthetic.EVIMO2_LOSS_CONFIG, 10)
+        w = dict(name="evimo2_300ms_b6_384x512_bezier10_tref10", B=batch or 6, K=10, basis="bezier",
                  median=events or 1_000_000, lognormal=False, deterministic=False, integer=True)
     elif variant == "k3_det":
         cfg = dict(synthetic.DSEC_LOSS_CONFIG)
@@ -693,7 +699,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="dsec", choices=["dsec", "dsec_tref5", "evimo2", "k3_det"])
+    ap.add_argument("--variant", default="dsec",
+                    choices=["dsec", "dsec_tref5", "evimo2", "evimo2_tref10", "k3_det"])
     ap.add_argument("--events", type=int, default=None, help="events per window (default: lognormal ~1e6)")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--dist", default="uniform", choices=["uniform", "edges"],

@@ -33,8 +33,8 @@ def main():
     ev, npos = device_batch(1, M, H, W, cfg["num_bins"], dev, seed=99)         # same window on every rank
     cg = synthetic.make_coeff_grid(1, 1, H, W, sigma_px=8.0, seed=1234).to(dev)
     out = {}
-    for det in (True, False):
-        L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=det))
+    for det, norm in ((True, "l1"), (False, "l1"), (False, "l2")):
+        L = LossFactory.get_loss_calculator("FOCUS", dict(cfg, deterministic=det, focus_loss_norm=norm))
         times = L.get_reconstruction_times(dev)
         times[0] = 0.5
         sh, np_r = shard_event_rows(ev, npos, rank, world)
@@ -63,10 +63,27 @@ def main():
             # float atomics: loss and IWE to 1e-5; the gradient of the l1 focus norm contains
             # sign(Sobel) of ~0 responses, which flips with the summation order (reported only)
             same = rel[0] <= 1e-5 and rel[1] <= 1e-5
+            # Evidence for that statement: count the pixels whose Sobel sign differs between the two
+            # IWEs and bound their response; with the l2 norm (no sign in the backward) the gradients
+            # must agree like everything else.
+            kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], device=dev)[None, None]
+            def sob(im):
+                im = im.reshape(-1, 1, H, W)
+                return torch.nn.functional.conv2d(im, kx, padding=1), torch.nn.functional.conv2d(im, kx.transpose(2, 3), padding=1)
+            (ax, ay), (bx, by) = sob(a_[1]), sob(b_[1])
+            fx, fy = torch.sign(ax) != torch.sign(bx), torch.sign(ay) != torch.sign(by)
+            scale = (ax.abs().mean() + ay.abs().mean()) / 2
+            worst = max(float(ax[fx].abs().max()) if fx.any() else 0.0, float(ay[fy].abs().max()) if fy.any() else 0.0)
+            flips = {"sign_flipped_pixels": int((fx | fy).sum()), "pixels": int(fx.numel()),
+                     "largest_flipped_response_over_mean": worst / float(scale)}
+            if norm == "l2":
+                same = same and rel[2] <= 1e-5
         flag = torch.tensor([1.0 if same else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         res = {"matches_unsharded_on_every_rank": bool(flag.item()),
                "rel_err_loss_iwes_dcoeff_rank0": rel}
+        if not det:
+            res["sobel_sign_flips_between_sharded_and_unsharded_iwe"] = flips
         for name, fn in (("single_gpu_ms", full), ("sharded_ms", sharded)):
             for _ in range(3):
                 fn()
@@ -80,7 +97,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[name] = t.item()
         res["events_per_s_sharded"] = M / res["sharded_ms"] * 1e3
-        out["deterministic" if det else "float"] = res
+        out["deterministic" if det else f"float_{norm}_focus_norm"] = res
     if rank == 0:
         print(json.dumps({"world": world, "events_in_window": M, "results": out}))
     assert all(v["matches_unsharded_on_every_rank"] for v in out.values())

@@ -1,6 +1,9 @@
 """Event-count sweep (BASELINE.json configs[4]): loss fwd+bwd events/s vs events per window.
 Windows are generated on the device (uniform events, time sorted, loader layout).
     python scripts/sweep.py [--batch 1,14] [--events 1e5,...] > profiles/rXX_sweep.json
+Under torchrun (N ranks on one node) every rank runs the same sweep on its own windows; rank 0
+prints whole-job rows: time = max over ranks (CUDA events), events = sum over ranks (weak scaling,
+no collective on the data path).
 """
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -34,7 +37,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--layouts", default="plain,packed", help="plain = upstream [B,M,6]; packed = io.PackedEvents")
     a = ap.parse_args()
-    dev = torch.device("cuda:0")
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     cfg = dict(synthetic.DSEC_LOSS_CONFIG)
     H, W = cfg["image_shape"]
     L = LossFactory.get_loss_calculator("FOCUS", dict(cfg))
@@ -50,7 +60,7 @@ def main():
         for M in [int(float(x)) for x in a.events.split(",")]:
             if B * M * 24 > 40e9:
                 continue
-            ev, npos = device_batch(B, M, H, W, cfg["num_bins"], dev, seed=B * 1000 + 7)
+            ev, npos = device_batch(B, M, H, W, cfg["num_bins"], dev, seed=B * 1000 + 7 + 100000 * rank)
 
             for layout in a.layouts.split(","):
                 batch = {"events": ev, "num_pos_events": npos}
@@ -72,6 +82,8 @@ def main():
                     loss.backward()
                 for _ in range(3):
                     step()
+                if dist is not None:
+                    dist.barrier()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 cabi.load().cmax_stage_timing_enable(1)
@@ -82,21 +94,30 @@ def main():
                 st = cabi.stage_timing_read()
                 cabi.load().cmax_stage_timing_enable(0)
                 ms = e0.elapsed_time(e1) / a.steps
+                if dist is not None:
+                    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                    ms = tmax.item()
                 n_t, n, Q = 16, 19200, 15 * 19200
                 ev_bytes = (32 if layout == "packed" else 48) * B * M      # records are 16 B, read twice
                 bytes_alg = ev_bytes + 20 * B * 2 * H * W + 24 * B * Q + 16 * B * n_t * n
-                rows.append({"B": B, "events_per_window": M, "layout": layout, "ms_per_step": ms,
-                             "events_per_s": B * M / ms * 1e3, "algorithmic_GB": bytes_alg / 1e9,
+                rows.append({"n_gpus": world, "B": B, "events_per_window": M, "layout": layout, "ms_per_step": ms,
+                             "events_per_s": world * B * M / ms * 1e3, "algorithmic_GB": bytes_alg / 1e9,
                              "achieved_GBps": bytes_alg / ms / 1e6, "hbm_frac": bytes_alg / ms / 1e6 / peak,
                              "event_forward_ms": st["event_forward"][0] / max(st["event_forward"][1], 1),
                              "event_backward_ms": st["event_backward"][0] / max(st["event_backward"][1], 1),
                              "device_pack_ms": pack_ms})
-                print(json.dumps(rows[-1]), file=sys.stderr)
+                if rank == 0:
+                    print(json.dumps(rows[-1]), file=sys.stderr)
                 batch = None
                 pk = None
             del ev
             torch.cuda.empty_cache()
-    print(json.dumps({"peak_GBps": peak, "rows": rows}, indent=1))
+    if rank == 0:
+        print(json.dumps({"peak_GBps": peak, "n_gpus": world, "rows": rows}, indent=1))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
