@@ -293,34 +293,6 @@ __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
 // staged record: (y, x) and, when the LUT entry is fused into the selection, the flow to t_ref
 __device__ __forceinline__ float2 rec_flow(const float4 &r) { return make_float2(r.z, r.w); }
 
-// ---- bulk async copies (TMA engine, no tensor map): global -> shared, completion on an mbarrier ----
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-                 "r"(parity)
-                 : "memory");
-}
-
 // One candidate of the single-pass bracket scan, branch free (a branch per outcome splits every
 // warp: the three outcomes are about 55 % / 20 % / 25 % of the candidates):
 //   d <  lo        sure member: count it and (FUSED) add its flow

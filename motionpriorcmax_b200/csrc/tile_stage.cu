@@ -56,6 +56,34 @@ __device__ __forceinline__ void smem_add_fix(unsigned *lo, unsigned *hi, long lo
     if (h) atomicAdd(hi, h);
 }
 
+// Float mode: ONE 32-bit word per window pixel, votes in 2^-24 fixed point (a vote of the packed
+// layout is a bilinear weight in [0, 1]; its float32 rounding error is of the same size).  A word
+// wraps at 256.0: the wrap is seen in the value the atomic returns and carried to the global image
+// as one red of 256.0 - rare (dense edges), exact.  Half the ATOMS, half the shared memory, half
+// the zeroing and flushing of the two-word int64 form the deterministic mode keeps.
+constexpr float kFloatFixScale = 16777216.0f;        // 2^24
+__device__ __forceinline__ void smem_add_vote(unsigned *word, float v, float *carry_to)
+{
+    if (v > 0.0f) {
+        const unsigned x = __float2uint_rn(__fmul_rn(v, kFloatFixScale));
+        if (x) {
+            const unsigned old = atomicAdd(word, x);
+            if (old + x < old) atomicAdd(carry_to, 256.0f);
+        }
+    } else if (v < 0.0f) {
+        atomicAdd(carry_to, v);      // a fractional part of -1e-6 (event_image_converter.py:357): straight to HBM
+    }
+}
+
+// TMA reduce-add of a contiguous shared-memory run into global memory (float32): the flush of one
+// window row is one asynchronous bulk operation instead of 16 REDG.v4 issued by as many threads.
+__device__ __forceinline__ void bulk_reduce_add_f32(float *gdst, const float *ssrc, unsigned bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
 __device__ __forceinline__ long long smem_get_fix(const unsigned *lo, const unsigned *hi)
 {
     return (long long)(((unsigned long long)*hi << 32) | (unsigned long long)*lo);
@@ -390,8 +418,9 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *s_lo = reinterpret_cast<unsigned *>(smem_raw);          // [kWin * kWin] low words
-    unsigned *s_hi = s_lo + kWin * kWin;                              // [kWin * kWin] high words
+    unsigned *s_hi = s_lo + kWin * kWin;                              // [kWin * kWin] high words (DET only)
     __shared__ int s_org[2];
+    __shared__ int s_rowflag[kWin];                                   // float mode: rows that received a vote
 
     const Seg sg = cta_segment(g, seg_start, split);
     if (sg.a >= sg.e) return;
@@ -400,13 +429,16 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
     const int64_t HW = (int64_t)g.H * g.W;
     const float4 *recs = records + b * g.M;
     const bool use_win = sg.e - sg.a >= 64;              // tiny slices: global reds are cheaper
+    // rows of the window can go out as bulk reduce-adds when every row start is 16-byte aligned
+    const bool bulk_ok = !DET && (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(raw) & 15u) == 0);
 
     const int lut_base = (int)b * g.nb;
     for (int r = 0; r < g.R; ++r) {
         int oy = 0, ox = 0;
         if (use_win) {
-            for (int i = tid; i < kWin * kWin / 2; i += kTileThreads)
-                reinterpret_cast<uint4 *>(s_lo)[i] = make_uint4(0u, 0u, 0u, 0u);       // both arrays
+            for (int i = tid; i < (DET ? kWin * kWin / 2 : kWin * kWin / 4); i += kTileThreads)
+                reinterpret_cast<uint4 *>(s_lo)[i] = make_uint4(0u, 0u, 0u, 0u);       // both arrays when DET
+            if (tid < kWin) s_rowflag[tid] = 0;
             window_origin(g, lut, b, sg, r, s_org, &oy, &ox);       // ends with a barrier
         }
         // window entirely inside the image: every corner that is in the window is in bounds
@@ -415,6 +447,7 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
         const float wx0 = (float)ox, wx1 = (float)(ox + kWin - 1);
         const float tref = __ldg(times + r);
         const int64_t base = ((b * g.R + r) * g.P + sg.grp) * HW;
+        float *img = raw + base;
         for (int i = sg.a + tid; i < sg.e; i += kTileThreads) {
             const PackedEvent pe = unpack(ld_stream_f4(recs + i));
             if (pe.bin >= g.nb || pe.iy >= g.Hq || pe.ix >= g.Wq) continue;      // corrupt record
@@ -434,10 +467,12 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
             const bool in_win = y1 >= wy0 && y1 < wy1 && x1 >= wx0 && x1 < wx1;
             if (in_win && interior) {
                 const int p = ((int)y1 - oy) * kWin + ((int)x1 - ox);
+                float *gp = img + (int64_t)(int)y1 * g.W + (int)x1;      // the same pixel in HBM (carries)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int q = p + (k & 1) * kWin + (k >> 1);
-                    smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
+                    if (DET) smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
+                    else smem_add_vote(s_lo + q, v[k], gp + (k & 1) * g.W + (k >> 1));
                 }
                 continue;
             }
@@ -450,7 +485,8 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
                 for (int k = 0; k < 4; ++k) {
                     if (!ok[k]) continue;
                     const int q = p + (k & 1) * kWin + (k >> 1);
-                    smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
+                    if (DET) smem_add_fix(s_lo + q, s_hi + q, to_fix(v[k]));
+                    else smem_add_vote(s_lo + q, v[k], img + (int64_t)(c.y + (k & 1)) * g.W + c.x + (k >> 1));
                 }
             } else {
 #pragma unroll
@@ -477,24 +513,45 @@ event_forward_tile_kernel(const float4 *__restrict__ records, const int *__restr
                               (unsigned long long)v);
             }
         } else {
-            for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
-                const uint4 l4 = reinterpret_cast<const uint4 *>(s_lo)[i];
-                const uint4 h4 = reinterpret_cast<const uint4 *>(s_hi)[i];
-                if ((l4.x | l4.y | l4.z | l4.w | h4.x | h4.y | h4.z | h4.w) == 0u) continue;
-                const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));
-                if (gy < 0 || gy >= g.H) continue;
-                const unsigned lo[4] = {l4.x, l4.y, l4.z, l4.w}, hi[4] = {h4.x, h4.y, h4.z, h4.w};
-                float vv[4];
+            // words -> float32 in place (one rounding of the exact tile sum), note the rows in use
+            float *s_f = reinterpret_cast<float *>(s_lo);
+            for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {       // 16 threads per window row
+                const uint4 u = reinterpret_cast<const uint4 *>(s_lo)[i];
+                const bool any = (u.x | u.y | u.z | u.w) != 0u;
+                reinterpret_cast<float4 *>(s_f)[i] =
+                    make_float4((float)u.x * (1.0f / kFloatFixScale), (float)u.y * (1.0f / kFloatFixScale),
+                                (float)u.z * (1.0f / kFloatFixScale), (float)u.w * (1.0f / kFloatFixScale));
+                const unsigned m = __ballot_sync(0xffffffffu, any);
+                if ((tid & 15) == 0 && ((m >> (tid & 16)) & 0xffffu)) s_rowflag[i / (kWin / 4)] = 1;
+            }
+            if (bulk_ok) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> async proxy
+                __syncthreads();
+                if (tid < kWin && s_rowflag[tid]) {
+                    const int gy = oy + tid;
+                    const int c0 = max(0, -ox), c1 = min(kWin, g.W - ox);          // multiples of 4
+                    if (gy >= 0 && gy < g.H && c1 > c0)
+                        bulk_reduce_add_f32(img + (int64_t)gy * g.W + ox + c0, s_f + tid * kWin + c0,
+                                            (unsigned)(c1 - c0) * 4u);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // window reusable / CTA may exit
+            } else {
+                __syncthreads();
+                for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
+                    const float4 vv = reinterpret_cast<const float4 *>(s_f)[i];
+                    if (vv.x == 0.0f && vv.y == 0.0f && vv.z == 0.0f && vv.w == 0.0f) continue;
+                    const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));
+                    if (gy < 0 || gy >= g.H) continue;
+                    const int64_t idx = base + (int64_t)gy * g.W + gx;
+                    const float q4[4] = {vv.x, vv.y, vv.z, vv.w};
+                    if (gx >= 0 && gx + 3 < g.W && (idx & 3) == 0) {
+                        red_add_f32x4(raw + idx, q4[0], q4[1], q4[2], q4[3]);
+                    } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)          // one rounding of the exact tile sum
-                    vv[k] = __ll2float_rn(smem_get_fix(lo + k, hi + k)) * (1.0f / 4294967296.0f);
-                const int64_t idx = base + (int64_t)gy * g.W + gx;
-                if (gx >= 0 && gx + 3 < g.W && (idx & 3) == 0) {
-                    red_add_f32x4(raw + idx, vv[0], vv[1], vv[2], vv[3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (vv[k] != 0.0f && gx + k >= 0 && gx + k < g.W) atomicAdd(raw + idx + k, vv[k]);
+                        for (int k = 0; k < 4; ++k)
+                            if (q4[k] != 0.0f && gx + k >= 0 && gx + k < g.W) atomicAdd(raw + idx + k, q4[k]);
+                    }
                 }
             }
         }
@@ -518,6 +575,8 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
     // dLUT block of the tile, [nb, ct, ct, 2] in 2^-32 fixed point: low words, then high words
     unsigned *s_alo = reinterpret_cast<unsigned *>(smem_raw + sizeof(float) * kWin * kWin);
     __shared__ int s_org[2];
+    __shared__ __align__(8) unsigned long long s_bar;       // completion of the bulk copies of the window
+    unsigned bar_phase = 0u;
 
     const Seg sg = cta_segment(g, seg_start, split);
     if (sg.a >= sg.e) return;
@@ -536,6 +595,7 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
         coef = __ldg(grad_loss) * (-(1.0f / (val * val))) / N;
     }
 
+    if (tid == 0) mbar_init(&s_bar, 1);                      // visible to all after window_origin's barrier
     const int lut_base = (int)b * g.nb;
     for (int r = 0; r < g.R; ++r) {
         const float *D = dimg + ((b * g.R + r) * g.P + sg.grp) * HW;
@@ -545,7 +605,23 @@ event_backward_tile_kernel(const float4 *__restrict__ records, const int *__rest
                 for (int i = tid; i < nacc * 4; i += kTileThreads) s_alo[i] = 0u;       // both arrays
             window_origin(g, lut, b, sg, r, s_org, &oy, &ox);
             // stage dL/dIWE of the window (zero outside the image)
-            if ((g.W & 3) == 0 && ((((b * g.R + r) * g.P + sg.grp) * HW) & 3) == 0) {
+            const bool aligned = (g.W & 3) == 0 && ((((b * g.R + r) * g.P + sg.grp) * HW) & 3) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(dimg) & 15u) == 0;
+            if (aligned && ox >= 0 && ox + kWin <= g.W) {
+                // every window row inside the image is one contiguous, 16-byte aligned run of 256 B:
+                // one bulk async copy per row (TMA engine, completion on the mbarrier); rows above /
+                // below the image are zero-filled by the threads
+                const int r_lo = min(max(0, -oy), kWin), r_hi = max(min(kWin, g.H - oy), r_lo);
+                if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(r_hi - r_lo) * kWin * 4u);
+                if (tid >= r_lo && tid < r_hi)
+                    bulk_g2s(s_D + tid * kWin, D + (int64_t)(oy + tid) * g.W + ox, kWin * 4u, &s_bar);
+                for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
+                    const int row = i / (kWin / 4);
+                    if (row < r_lo || row >= r_hi) reinterpret_cast<float4 *>(s_D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&s_bar, bar_phase);
+                bar_phase ^= 1u;
+            } else if (aligned) {
                 for (int i = tid; i < kWin * kWin / 4; i += kTileThreads) {
                     const int gy = oy + i / (kWin / 4), gx = ox + 4 * (i % (kWin / 4));   // ox % 4 == 0
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -675,7 +751,7 @@ int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *re
     if (g.M > 0) {
         const int split = pick_split(g);
         dim3 grid((unsigned)(g.nt * split), (unsigned)g.P, (unsigned)g.B);
-        const size_t sm = 2 * sizeof(unsigned) * kWin * kWin;
+        const size_t sm = (g.det ? 2 : 1) * sizeof(unsigned) * kWin * kWin;
         if (g.det)
             event_forward_tile_kernel<true><<<grid, kTileThreads, sm, st>>>(records, seg_start, times, g,
                                                                             split, lut, raw, raw_i64);
