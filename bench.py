@@ -338,6 +338,9 @@ def run_ours(args):
         torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host placement before any pinned allocation: this rank's staging buffers next to its GPU
+    from motionpriorcmax_b200.io import bind_host_to_device_numa
+    numa = {"bound": False, "skipped": "--no-numa"} if args.no_numa else bind_host_to_device_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -624,7 +627,8 @@ def run_ours(args):
                     "h2d_GBps_per_rank_copy_alone": (e2e_info.get("h2d_bytes", 0) / (copy_alone_ms * 1e-3) / 1e9)
                     if copy_alone_ms == copy_alone_ms else None,
                     "copy_alone_ms": copy_alone_ms, "host_issue_ms_per_step": host_issue_ms,
-                    "host_pack_s_per_batch_rank0": e2e_info.get("host_pack_s_per_batch")},
+                    "host_pack_s_per_batch_rank0": e2e_info.get("host_pack_s_per_batch"),
+                    "host_numa_binding_rank0": numa},
             "e2e_reference_layout": {
                 "value": ev_all / (ms_e2e_ref / args.steps * 1e-3), "unit": "events/s",
                 "ms_per_step": ms_e2e_ref / args.steps, "h2d_bytes_per_step": e2e_info.get("ref_h2d_bytes", 0),
@@ -710,6 +714,7 @@ def main():
     ap.add_argument("--no-packed", action="store_true", help="skip the packed-layout legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input legs (profiling runs)")
     ap.add_argument("--no-train", action="store_true", help="skip the UNet + DDP training-step leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     ap.add_argument("--prof-warmup", type=int, default=None, help="override the >=3 warm-up rule (ncu runs only)")
     args = ap.parse_args()
     if args.impl == "reference":

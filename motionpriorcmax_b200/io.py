@@ -488,3 +488,56 @@ class CompactUploader:
 
     def release(self, slot: int, stream=None):
         self.free[slot].record(stream or torch.cuda.current_stream(self.device))
+
+
+# ------------------------------------------------------------------------------------------------
+# host placement: keep a rank's pinned staging buffers on the NUMA node of its GPU
+# ------------------------------------------------------------------------------------------------
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_device_numa(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that the pinned
+    buffers it allocates afterwards (first touch) and the loader-side packing sit next to that GPU's
+    PCIe root.  With one process per GPU on a two-socket host this keeps N concurrent host->device
+    streams off the inter-socket link.  Best effort: returns what it found / did, never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = vis.split(",")
+            if device_index < len(ids) and ids[device_index].strip().isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                     # nvml prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        info["pci_bus_id"] = bus
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:                                 # no NUMA information, containers, ...
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
