@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--layouts", default="plain,packed", help="plain = upstream [B,M,6]; packed = io.PackedEvents")
     a = ap.parse_args()
+    real_stdout = os.fdopen(os.dup(1), "w")      # libraries print banners to stdout (NCCL): keep fd 1 for the JSON
+    os.dup2(2, 1)
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -114,7 +116,7 @@ def main():
             del ev
             torch.cuda.empty_cache()
     if rank == 0:
-        print(json.dumps({"peak_GBps": peak, "n_gpus": world, "rows": rows}, indent=1))
+        print(json.dumps({"peak_GBps": peak, "n_gpus": world, "rows": rows}, indent=1), file=real_stdout, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
