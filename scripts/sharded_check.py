@@ -78,6 +78,13 @@ def main():
                      "largest_flipped_response_over_mean": worst / float(scale)}
             if norm == "l2":
                 same = same and rel[2] <= 1e-5
+            # the yardstick for the l1 gradient: two UNSHARDED float runs differ from each other by the
+            # same amount (float atomics commute differently from run to run; sign(Sobel) of responses
+            # that cancel to ~0 follows the last bits).  Not a property of the sharding.
+            c_ = full()
+            torch.cuda.synchronize()
+            flips["unsharded_run_to_run_rel_diff_dcoeff"] = ((a_[2] - c_[2]).norm() / a_[2].norm()).item()
+            flips["unsharded_run_to_run_rel_diff_iwes"] = ((a_[1] - c_[1]).norm() / a_[1].norm()).item()
         flag = torch.tensor([1.0 if same else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         res = {"matches_unsharded_on_every_rank": bool(flag.item()),

@@ -617,6 +617,47 @@ def test_ten_reference_times():
     assert rel_err(r["dtraj"], g["dtraj"]) < 2 * TOL
 
 
+def test_full_size_evimo2_ten_reference_times_matches_oracle():
+    """The "10 reference times" variant of BASELINE.json configs[2] at its own size: 384x512, 41
+    bins, Bezier degree 10 (x-major parameters), n_tref = 10 with the only combination focus.py:49-51
+    allows (no polarity split, no dt scaling, smoothness on flow_to_tref), one window, against the
+    float64 oracle (the as-shipped l1 focus norm: the gradient check may take the bounded sign
+    fallback)."""
+    from motionpriorcmax_b200 import synthetic, trajectories as tj
+    from motionpriorcmax_b200.losses import LossFactory
+    from oracle import focus_oracle as fo
+    dev = _cuda()
+    cfg = synthetic.multi_tref_variant(synthetic.EVIMO2_LOSS_CONFIG, 10)
+    H, W = cfg["image_shape"]
+    deg, B = 10, 1
+    times = fo.reconstruction_times(10, cfg["num_bins"])
+    cg = synthetic.make_coeff_grid(B, deg, H, W, sigma_px=5.0, seed=33, coarse=(6, 8))   # [B,1,20,H,W]
+    ev, npos = synthetic.make_event_batch(B, [120_000], H, W, cfg["num_bins"], False, seed=33,
+                                          integer_coords=True, coord_scale=0.8)
+    L = LossFactory.get_loss_calculator("FOCUS", dict(cfg))
+    cgd = cg.to(dev).requires_grad_()
+    tm = torch.as_tensor(times, device=dev)
+    traj = tj.calculate_trajectories_at_t(cgd, tm, 4, deg, "bezier", xy_order=True)
+    loss, log, misc = L.calc(traj, tm, {"events": ev.to(dev)}, return_flow_lut=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    tr_ref, _ = fo.trajectories_from_coeff_grid(cg.numpy(), times, 4, deg, "bezier", xy_order=True)
+    o = fo.FocusOracle(**cfg, dtype=np.float64)
+    f = o.forward(tr_ref, times, ev.numpy(), -1)
+    g = o.backward()
+    assert misc["iwes"].shape == (B, 10, H, W)
+    assert abs(loss.item() - f["loss"]) <= TOL * abs(f["loss"])
+    assert abs(log["smoothness_loss"].item() - f["smoothness_loss"]) <= TOL * abs(f["smoothness_loss"])
+    assert rel_err(misc["flow_lut"].cpu().numpy(), f["flow_lut"]) < TOL
+    assert rel_err(misc["iwes"].cpu().numpy(), f["iwes"]) < TOL
+    # gradient w.r.t. the trajectories first (shared checker with the bounded l1 fallback), then the
+    # front end's adjoint on the oracle's trajectory gradient
+    t2 = traj.detach().clone().requires_grad_()
+    L.calc(t2, tm, {"events": ev.to(dev)})[0].backward()
+    _assert_grad_close(t2.grad.cpu().numpy(), g["dtraj"], cfg, tr_ref, times, ev.numpy(), -1,
+                       gpu_iwes=misc["iwes"].cpu().numpy())
+
+
 @pytest.mark.timeout(120)
 def test_non_finite_trajectories_do_not_hang():
     """Diverged training can hand NaN / Inf trajectories to the loss; the kernels must terminate
