@@ -485,7 +485,12 @@ def run_ours(args):
         t0 = time.perf_counter()
         comp_h = cio.pack_events_compact(ev_h, npos, L)             # loader side, outside the step
         pack_s = time.perf_counter() - t0
-        comp_p = comp_h.pin_memory()
+        try:
+            comp_p = comp_h.pin_memory(write_combined=True)
+            e2e_host_mem = "cudaHostAllocWriteCombined"
+        except Exception:
+            comp_p = comp_h.pin_memory()
+            e2e_host_mem = "pinned"
         cup = cio.CompactUploader(dev, L, n_buffers=NBUF)
         ms_e2e = time_e2e(lambda: cup.upload(comp_p), cup)
         ms_e2e_cg = time_e2e(lambda: cup.upload(comp_p), cup, cg_from_host=True)
@@ -628,7 +633,7 @@ def run_ours(args):
                     if copy_alone_ms == copy_alone_ms else None,
                     "copy_alone_ms": copy_alone_ms, "host_issue_ms_per_step": host_issue_ms,
                     "host_pack_s_per_batch_rank0": e2e_info.get("host_pack_s_per_batch"),
-                    "host_numa_binding_rank0": numa},
+                    "host_numa_binding_rank0": numa, "host_buffer": e2e_host_mem if not args.no_e2e else None},
             "e2e_reference_layout": {
                 "value": ev_all / (ms_e2e_ref / args.steps * 1e-3), "unit": "events/s",
                 "ms_per_step": ms_e2e_ref / args.steps, "h2d_bytes_per_step": e2e_info.get("ref_h2d_bytes", 0),
