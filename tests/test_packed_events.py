@@ -409,9 +409,15 @@ def test_packed_slices_empty_and_padding():
         b = _run(cfg, traj, times, ev2, npos, mode, True)
         assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
         assert b["packed"].seg_start[:, -1].tolist() == [int(ev2[0, :, 5].sum()), 0]
+    b = _run(cfg, traj, times, ev2, npos, "compact", True)          # the 12-byte wire layout, sliced segments
+    assert a["loss"] == b["loss"] and np.array_equal(a["iwes"], b["iwes"]) and np.array_equal(a["dtraj"], b["dtraj"])
+    assert b["packed"].sample_off.tolist() == [0, int(ev2[0, :, 5].sum()), int(ev2[0, :, 5].sum())]
     # M = 0: no event kernel runs; 1 / mean(0) = inf like the reference
     c = _run(cfg, traj, times, ev[:, :0], 0, "packed_dev")
     assert np.isinf(c["loss"]) and np.abs(c["iwes"]).max() == 0.0
+    # every window empty / all padding through the compact layout (T = 0: nothing crosses PCIe)
+    c = _run(cfg, traj, times, np.zeros_like(ev), npos, "compact")
+    assert np.isinf(c["loss"]) and np.abs(c["iwes"]).max() == 0.0 and int(c["packed"].sample_off[-1]) == 0
 
 
 @pytest.mark.gpu
