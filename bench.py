@@ -13,9 +13,9 @@ Default workload = BASELINE.json configs[1]: DSEC training shape, per-rank batch
 Printed JSON line (rank 0): see the keys below; `value` = valid events of all ranks per second
 with inputs resident in HBM (CUDA events, max over ranks); `e2e` = same metric through the
 plugin API with pinned HOST inputs copied in (double-buffered) and the loss read back, every
-step inside the timed region - the host buffer is the loader-side `io.CompactEvents` (12 bytes
-per valid event, one cudaMemcpyAsync per step; built by the loader workers outside the step like
-the reference's own collate), `e2e_reference_layout` is the same leg on the reference's padded
+step inside the timed region - the host buffer is the loader-side `io.BitpackedEvents` (a lossless
+~8-byte-per-event bit stream, one cudaMemcpyAsync per step; built by the loader workers outside the
+step like the reference's own collate; `e2e.compact_12B_layout` = the uncompressed 12-byte form), `e2e_reference_layout` is the same leg on the reference's padded
 `[B, M, 6]` tensor; `train_step` = UNet(15, 2K) forward -> front end -> loss -> backward ->
 AdamW under DDP (NCCL all-reduce of the 31 M network gradients inside the timed region);
 `roofline` = dominant kernel (by measured stage time) against the HBM peak of
@@ -483,23 +483,23 @@ def run_ours(args):
     e2e_info = {}
     if not args.no_e2e:
         t0 = time.perf_counter()
-        comp_h = cio.pack_events_compact(ev_h, npos, L)             # loader side, outside the step
+        wire_h = cio.pack_events_bitpacked(ev_h, npos, L)           # loader side, outside the step
         pack_s = time.perf_counter() - t0
         try:
-            comp_p = comp_h.pin_memory(write_combined=True)
+            wire_p = wire_h.pin_memory(write_combined=True)
             e2e_host_mem = "cudaHostAllocWriteCombined"
         except Exception:
-            comp_p = comp_h.pin_memory()
+            wire_p = wire_h.pin_memory()
             e2e_host_mem = "pinned"
         cup = cio.CompactUploader(dev, L, n_buffers=NBUF)
-        ms_e2e = time_e2e(lambda: cup.upload(comp_p), cup)
-        ms_e2e_cg = time_e2e(lambda: cup.upload(comp_p), cup, cg_from_host=True)
+        ms_e2e = time_e2e(lambda: cup.upload(wire_p), cup)
+        ms_e2e_cg = time_e2e(lambda: cup.upload(wire_p), cup, cg_from_host=True)
         # copy alone (no compute in flight): what PCIe gives this rank
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record(cup.stream)
         for _ in range(5):
-            _, sl = cup.upload(comp_p)
+            _, sl = cup.upload(wire_p)
             cup.release(sl, cup.stream)
         c1.record(cup.stream)
         barrier()
@@ -507,6 +507,12 @@ def run_ours(args):
         e2e_info = {"h2d_bytes": int(cup.bytes_last), "host_issue_ms": cup.issue_ms_last,
                     "copy_alone_ms": copy_ms, "host_pack_s_per_batch": pack_s,
                     "cg_bytes": int(cg_p.numel() * 4), "ms_with_cg": ms_e2e_cg}
+        # the uncompressed 12-byte wire layout for comparison
+        comp_p = cio.pack_events_compact(ev_h, npos, L).pin_memory()
+        cup12 = cio.CompactUploader(dev, L, n_buffers=NBUF)
+        e2e_info["ms_compact12"] = time_e2e(lambda: cup12.upload(comp_p), cup12)
+        e2e_info["compact12_bytes"] = int(cup12.bytes_last)
+        del comp_p, cup12
         ev_p = ev_h.pin_memory()
         up = EventUploader(dev, n_buffers=NBUF)
         ms_e2e_ref = time_e2e(lambda: up.upload(ev_p, npos), up)
@@ -619,12 +625,17 @@ def run_ours(args):
                          "knn_worklist_cells": worklist},
             "e2e": {"value": e2e_val, "unit": "events/s",
                     "h2d_bytes_per_step": e2e_info.get("h2d_bytes", 0),
-                    "h2d_note": "the step's host input = the event windows the loader delivers, as io.CompactEvents: "
-                                "12 B per valid event + run tables, one cudaMemcpyAsync per step from pinned "
-                                "memory, expanded to 16-byte records on the device (cmax_expand_compact); built by "
-                                "the loader workers outside the step.  The coefficient grid is the network's "
-                                "output and stays on the device (see train_step); with_coeff_grid_from_host ships "
-                                "it over PCIe as well, every step",
+                    "h2d_note": "the step's host input = the event windows the loader delivers, as io.BitpackedEvents: "
+                                "a LOSSLESS bit stream of per-run bit-pattern deltas of (y, x, t), ~8.2 B per valid "
+                                "event + run tables, one cudaMemcpyAsync per step from pinned memory, decoded to "
+                                "16-byte records on the device (cmax_expand_bitpacked); built by the loader "
+                                "workers outside the step.  The coefficient grid is the network's output and stays "
+                                "on the device (see train_step); with_coeff_grid_from_host ships it over PCIe as "
+                                "well, every step; compact_12B_layout is the same leg on the uncompressed 12-byte "
+                                "wire layout (io.CompactEvents)",
+                    "compact_12B_layout": {
+                        "ms_per_step_rank0": e2e_info.get("ms_compact12", float("nan")) / args.steps,
+                        "h2d_bytes_per_step": e2e_info.get("compact12_bytes", 0)},
                     "with_coeff_grid_from_host": {
                         "ms_per_step_rank0": e2e_info.get("ms_with_cg", float("nan")) / args.steps,
                         "h2d_bytes_per_step": e2e_info.get("h2d_bytes", 0) + e2e_info.get("cg_bytes", 0)},

@@ -152,6 +152,27 @@ int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_
                         const int64_t *sample_off, int64_t B, int64_t records_stride,
                         float *records_out, int32_t *seg_start_out, void *stream);
 
+/* Bit-packed wire layout: the runs of the compact layout, every run stored as fixed-width records of
+ * bit-pattern deltas (inside one (group, tile, bin) run y, x and t vary little, and the IEEE bit
+ * pattern of a non-negative float is monotone): field = bits(value) - min over the run, in
+ * w = bit_length(max - min) bits, w = 0..32 per field.  LOSSLESS for any float32 input; about 8 B per
+ * event for a DSEC window instead of 12.
+ *   words    [total] uint32: the windows' bit streams back to back, window b at word_off[b]
+ *            (int64 [B + 1]; two zero words of slack end every window's stream);
+ *   run_hdr  [B, F, 4] uint32 (F = G * NT * nb): min patterns of y, x, t and wy | wx << 8 | wt << 16;
+ *   run_word [B, F + 1] int32: first word of every run inside its window's stream (runs are word
+ *            aligned); fine_start [B, F + 1] as in the compact layout.
+ * cmax_pack_events_host_bitpacked (HOST pointers; first call with words_host = NULL for the sizes),
+ * cmax_expand_bitpacked (DEVICE pointers): decodes into the packed layout, bit for bit the records
+ * cmax_expand_compact produces. */
+int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const float *events_host, int64_t B, int64_t M,
+                                    int64_t num_pos_events, uint32_t *words_host, int64_t words_capacity,
+                                    int32_t *fine_start_host, uint32_t *run_hdr_host, int32_t *run_word_host,
+                                    int64_t *word_off_host, int64_t *skipped_host);
+int cmax_expand_bitpacked(const CmaxConfig *cfg, const uint32_t *words, const int32_t *fine_start,
+                          const uint32_t *run_hdr, const int32_t *run_word, const int64_t *word_off, int64_t B,
+                          int64_t records_stride, float *records_out, int32_t *seg_start_out, void *stream);
+
 /* cmax_forward / cmax_backward on the packed layout: same outputs, same workspace
  * (cmax_workspace_bytes(cfg, B, M, n) with the M of `records`).  The event stage accumulates
  * the IWE votes of a (tile, group) segment in a shared-memory window and flushes once; votes

@@ -213,6 +213,7 @@ Layout make_layout(const Geom &g)
 // (already phi(t) - phi(anchor)) broadcast from shared memory.
 constexpr int kMaxBasis = 16;
 
+template <int KB>       // register budget for the coefficients: 4 (polynomial K <= 4) or kMaxBasis
 __global__ void __launch_bounds__(128)
 traj_forward_kernel(const float *__restrict__ cg, const float *__restrict__ phi, int64_t S, int K,
                     int H, int W, int patch, int ny, int nx, int n_t, int xy, int add_off,
@@ -227,10 +228,10 @@ traj_forward_kernel(const float *__restrict__ cg, const float *__restrict__ phi,
     if (j >= n) return;
     const int ty = (int)(j / nx), tx = (int)(j - (int64_t)ty * nx);
     const int py = patch / 2 + ty * patch, px = patch / 2 + tx * patch;     // trajectories.py:8-13
-    float cy[kMaxBasis], cx[kMaxBasis];
+    float cy[KB], cx[KB];
     const int64_t HW = (int64_t)H * W;
 #pragma unroll
-    for (int k = 0; k < kMaxBasis; ++k) {
+    for (int k = 0; k < KB; ++k) {
         if (k < K) {
             float a0 = 0.0f, a1 = 0.0f;
             for (int64_t sc = 0; sc < S; ++sc) {                        // sum over scales (basis.py:46)
@@ -246,7 +247,7 @@ traj_forward_kernel(const float *__restrict__ cg, const float *__restrict__ phi,
     for (int t = 0; t < n_t; ++t) {
         float y = 0.0f, x = 0.0f;
 #pragma unroll
-        for (int k = 0; k < kMaxBasis; ++k)
+        for (int k = 0; k < KB; ++k)
             if (k < K) {
                 y += s_phi[t * K + k] * cy[k];
                 x += s_phi[t * K + k] * cx[k];
@@ -256,6 +257,7 @@ traj_forward_kernel(const float *__restrict__ cg, const float *__restrict__ phi,
     }
 }
 
+template <int KB>
 __global__ void __launch_bounds__(128)
 traj_backward_kernel(const float *__restrict__ dtraj, const float *__restrict__ phi, int64_t S,
                      int K, int H, int W, int patch, int ny, int nx, int n_t, int xy,
@@ -270,14 +272,14 @@ traj_backward_kernel(const float *__restrict__ dtraj, const float *__restrict__ 
     if (j >= n) return;
     const int ty = (int)(j / nx), tx = (int)(j - (int64_t)ty * nx);
     const int py = patch / 2 + ty * patch, px = patch / 2 + tx * patch;
-    float gy[kMaxBasis], gx[kMaxBasis];
+    float gy[KB], gx[KB];
 #pragma unroll
-    for (int k = 0; k < kMaxBasis; ++k) gy[k] = gx[k] = 0.0f;
+    for (int k = 0; k < KB; ++k) gy[k] = gx[k] = 0.0f;
     const float2 *d = reinterpret_cast<const float2 *>(dtraj) + b * (int64_t)n_t * n + j;
     for (int t = 0; t < n_t; ++t) {
         const float2 v = __ldg(d + (int64_t)t * n);
 #pragma unroll
-        for (int k = 0; k < kMaxBasis; ++k)
+        for (int k = 0; k < KB; ++k)
             if (k < K) {
                 gy[k] += s_phi[t * K + k] * v.x;
                 gx[k] += s_phi[t * K + k] * v.y;
@@ -285,7 +287,7 @@ traj_backward_kernel(const float *__restrict__ dtraj, const float *__restrict__ 
     }
     const int64_t HW = (int64_t)H * W;
 #pragma unroll
-    for (int k = 0; k < kMaxBasis; ++k) {
+    for (int k = 0; k < KB; ++k) {
         if (k < K) {
             for (int64_t sc = 0; sc < S; ++sc) {
                 float *base = dcg + ((b * S + sc) * 2 * K) * HW + (int64_t)py * W + px;
@@ -581,6 +583,25 @@ int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_
                                  static_cast<cudaStream_t>(stream));
 }
 
+int cmax_expand_bitpacked(const CmaxConfig *cfg, const uint32_t *words, const int32_t *fine_start,
+                          const uint32_t *run_hdr, const int32_t *run_word, const int64_t *word_off, int64_t B,
+                          int64_t records_stride, float *records_out, int32_t *seg_start_out, void *stream)
+{
+    DeviceGuard dev_guard(seg_start_out);
+    Geom g;
+    int rc = make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g);
+    if (rc != CMAX_OK) return rc;
+    if ((rc = pack_supported(g))) return rc;
+    if (!fine_start || !run_hdr || !run_word || !word_off || !seg_start_out ||
+        (records_stride > 0 && (!words || !records_out)))
+        return CMAX_ERR_BAD_SHAPE;
+    if (((uintptr_t)records_out & 15u) || ((uintptr_t)run_hdr & 15u)) return CMAX_ERR_WORKSPACE;
+    return launch_expand_bitpacked(g, words, fine_start, run_hdr, run_word,
+                                   reinterpret_cast<const long long *>(word_off), records_stride,
+                                   reinterpret_cast<float4 *>(records_out), seg_start_out,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 int cmax_forward_packed(const CmaxConfig *cfg, const float *trajectories, const float *times,
                         const float *records, const int32_t *seg_start, int64_t B, int64_t M,
                         int64_t n, float *iwes_out, float *losses_out, float *flow_lut_out,
@@ -734,8 +755,12 @@ int cmax_trajectories_forward(const float *coeff_grid, const float *phi, int64_t
     dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
     StageScope sc(ST_TRAJ_FWD, static_cast<cudaStream_t>(stream));
     count_launch();
-    traj_forward_kernel<<<grid, 128, sizeof(float) * n_t * K, static_cast<cudaStream_t>(stream)>>>(
-        coeff_grid, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, add_offsets, trajectories_out);
+    if (K <= 4)       // 8 instead of 32 coefficient registers: twice the resident warps for the common orders
+        traj_forward_kernel<4><<<grid, 128, sizeof(float) * n_t * K, static_cast<cudaStream_t>(stream)>>>(
+            coeff_grid, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, add_offsets, trajectories_out);
+    else
+        traj_forward_kernel<kMaxBasis><<<grid, 128, sizeof(float) * n_t * K, static_cast<cudaStream_t>(stream)>>>(
+            coeff_grid, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, add_offsets, trajectories_out);
     return check_launch();
 }
 
@@ -754,8 +779,12 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
     dim3 grid((unsigned)(((int64_t)ny * nx + 127) / 128), (unsigned)B);
     StageScope sc(ST_TRAJ_BWD, st);
     count_launch();
-    traj_backward_kernel<<<grid, 128, sizeof(float) * n_t * K, st>>>(
-        dtraj, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, dcoeff_grid_out);
+    if (K <= 4)
+        traj_backward_kernel<4><<<grid, 128, sizeof(float) * n_t * K, st>>>(
+            dtraj, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, dcoeff_grid_out);
+    else
+        traj_backward_kernel<kMaxBasis><<<grid, 128, sizeof(float) * n_t * K, st>>>(
+            dtraj, phi, S, K, H, W, patch, ny, nx, n_t, xy_order, dcoeff_grid_out);
     return check_launch();
 }
 

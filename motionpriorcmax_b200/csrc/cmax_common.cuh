@@ -78,6 +78,9 @@ int launch_pack_events(const Geom &g, const float *events, float4 *records, int 
 int launch_expand_compact(const Geom &g, const float *coords, const int *fine_start,
                           const long long *sample_off, int64_t Mp, float4 *records, int *seg_start,
                           cudaStream_t st);
+int launch_expand_bitpacked(const Geom &g, const unsigned *words, const int *fine_start, const unsigned *run_hdr,
+                            const int *run_word, const long long *word_off, int64_t Mp, float4 *records,
+                            int *seg_start, cudaStream_t st);
 int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
                                 const int *seg_start, const float *times, char *ws, cudaStream_t st);
 int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *records,

@@ -232,6 +232,25 @@ pack_scatter_kernel(const float *__restrict__ events, Geom g, int *__restrict__ 
                 make_float4(ry[u], rx[u], rt[u], __uint_as_float(meta[u]));
 }
 
+// Run of record i in a window's fine_start table (last run whose start is <= i).  The 32 records of
+// a warp are consecutive and a run holds ~100 records: lane 0 does the binary search, the other
+// lanes walk forward from its answer (one to three steps) instead of 14 dependent loads each.
+__device__ __forceinline__ int run_of(const int *__restrict__ fs, int F, int i, int count)
+{
+    int lo = 0;
+    if ((threadIdx.x & 31) == 0 && i < count) {
+        int hi = F - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(fs + mid) <= i) lo = mid; else hi = mid - 1;
+        }
+    }
+    lo = __shfl_sync(0xffffffffu, lo, 0);
+    if (i < count)
+        while (lo + 1 < F && __ldg(fs + lo + 1) <= i) ++lo;
+    return lo;
+}
+
 // ---------------------------------------------------------------------------------------------
 // compact wire layout (12 B per event, host packed) -> packed records + seg_start
 // ---------------------------------------------------------------------------------------------
@@ -250,12 +269,8 @@ expand_compact_kernel(const float *__restrict__ coords, const int *__restrict__ 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= g.P * g.nt)                                   // coarse table: every nb-th fine entry
         seg_start[(int64_t)b * (g.P * g.nt + 1) + i] = __ldg(fs + i * g.nb);
+    const int lo = run_of(fs, F, (int)min(i, (int64_t)INT32_MAX), count);    // (whole warps enter: shuffles inside)
     if (i >= count) return;
-    int lo = 0, hi = F - 1;                                // last run whose start is <= i
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(fs + mid) <= (int)i) lo = mid; else hi = mid - 1;
-    }
     const int bin = lo % g.nb;
     const float *c = coords + (__ldg(sample_off + b) + i) * 3;
     const float y = __ldg(c), x = __ldg(c + 1), t = __ldg(c + 2);
@@ -274,6 +289,61 @@ int launch_expand_compact(const Geom &g, const float *coords, const int *fine_st
     StageScope sc(ST_PACK, st);
     count_launch();
     expand_compact_kernel<<<grid, 256, 0, st>>>(coords, fine_start, sample_off, g, Mp, records, seg_start);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit-packed wire layout (host_pack.cpp: fixed-width bit-pattern deltas per run) -> packed records
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned bit_field(const unsigned *__restrict__ words, unsigned long long bit, int w)
+{
+    if (w == 0) return 0u;
+    const unsigned long long wi = bit >> 5;
+    const unsigned v = __funnelshift_r(__ldg(words + wi), __ldg(words + wi + 1), (unsigned)(bit & 31u));
+    return w >= 32 ? v : (v & ((1u << w) - 1u));
+}
+
+__global__ void __launch_bounds__(256)
+expand_bitpacked_kernel(const unsigned *__restrict__ words_all, const int *__restrict__ fine_start,
+                        const uint4 *__restrict__ run_hdr, const int *__restrict__ run_word,
+                        const long long *__restrict__ word_off, Geom g, int64_t Mp,
+                        float4 *__restrict__ records, int *__restrict__ seg_start)
+{
+    const int b = blockIdx.y;
+    const int F = g.P * g.nt * g.nb;
+    const int *fs = fine_start + (int64_t)b * (F + 1);
+    const int count = __ldg(fs + F);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= g.P * g.nt) seg_start[(int64_t)b * (g.P * g.nt + 1) + i] = __ldg(fs + i * g.nb);
+    const int lo = run_of(fs, F, (int)min(i, (int64_t)INT32_MAX), count);    // (whole warps enter: shuffles inside)
+    if (i >= count) return;
+    const uint4 h = __ldg(run_hdr + (int64_t)b * F + lo);
+    const int wy = (int)(h.w & 255u), wx = (int)((h.w >> 8) & 255u), wt = (int)((h.w >> 16) & 255u);
+    const unsigned *words = words_all + __ldg(word_off + b);
+    unsigned long long bit = (unsigned long long)__ldg(run_word + (int64_t)b * (F + 1) + lo) * 32ull +
+                             (unsigned long long)((int)i - __ldg(fs + lo)) * (unsigned)(wy + wx + wt);
+    const float y = __uint_as_float(h.x + bit_field(words, bit, wy));
+    bit += (unsigned)wy;
+    const float x = __uint_as_float(h.y + bit_field(words, bit, wx));
+    bit += (unsigned)wx;
+    const float t = __uint_as_float(h.z + bit_field(words, bit, wt));
+    const int bin = lo % g.nb;
+    const float fsz = (float)g.s;
+    const int iy = (int)floordiv_f32(y, fsz), ix = (int)floordiv_f32(x, fsz);
+    const unsigned meta = ((unsigned)bin << 24) | ((unsigned)iy << 12) | (unsigned)ix;
+    records[(int64_t)b * Mp + i] = make_float4(y, x, t, __uint_as_float(meta));
+}
+
+int launch_expand_bitpacked(const Geom &g, const unsigned *words, const int *fine_start, const unsigned *run_hdr,
+                            const int *run_word, const long long *word_off, int64_t Mp, float4 *records,
+                            int *seg_start, cudaStream_t st)
+{
+    const int64_t span = Mp > g.P * g.nt + 1 ? Mp : g.P * g.nt + 1;
+    dim3 grid((unsigned)((span + 255) / 256), (unsigned)g.B);
+    StageScope sc(ST_PACK, st);
+    count_launch();
+    expand_bitpacked_kernel<<<grid, 256, 0, st>>>(words, fine_start, reinterpret_cast<const uint4 *>(run_hdr), run_word,
+                                                  word_off, g, Mp, records, seg_start);
     return check_launch();
 }
 

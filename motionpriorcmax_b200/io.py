@@ -19,6 +19,9 @@ coordinates), all windows of a batch back to back in ONE pinned buffer, so a ste
 PCIe in one `cudaMemcpyAsync`.  `pack_events_compact` builds it in the loader workers (C++ /
 OpenMP), `CompactUploader` copies it (double buffered) and rebuilds the 16-byte records on the
 device with one kernel (`cmax_expand_compact`); `FocusLoss.calc` also accepts it directly.
+`BitpackedEvents` shrinks the wire form further, losslessly: every (group, tile, bin) run stores
+fixed-width bit-pattern deltas of (y, x, t) - about 8 bytes per event for a DSEC window - decoded by
+`cmax_expand_bitpacked` into the very same records.
 """
 from __future__ import annotations
 
@@ -469,48 +472,159 @@ def expand_compact(compact: CompactEvents, loss_or_cfg, out: Optional[PackedEven
     return out
 
 
+@dataclass
+class BitpackedEvents:
+    """Bit-packed wire layout (include/cmax_b200.h): words [total] int32 (bit stream), fine_start
+    [B, F + 1] int32, run_hdr [B, F, 4] int32, run_word [B, F + 1] int32, word_off [B + 1] int64."""
+    words: torch.Tensor
+    fine_start: torch.Tensor
+    run_hdr: torch.Tensor
+    run_word: torch.Tensor
+    word_off: torch.Tensor
+    max_count: int
+    skipped: Optional[torch.Tensor] = None
+
+    _TENSORS = ("words", "fine_start", "run_hdr", "run_word", "word_off")
+
+    @property
+    def is_cuda(self):
+        return self.words.is_cuda
+
+    @property
+    def device(self):
+        return self.words.device
+
+    def num_events(self) -> torch.Tensor:
+        return self.fine_start[:, -1]
+
+    def nbytes(self) -> int:
+        return int(sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self._TENSORS))
+
+    def to(self, device, non_blocking: bool = False):
+        return BitpackedEvents(*(getattr(self, k).to(device, non_blocking=non_blocking) for k in self._TENSORS),
+                               self.max_count, self.skipped)
+
+    def pin_memory(self, write_combined: bool = False):
+        words = pinned_write_combined_copy(self.words) if write_combined else self.words.pin_memory()
+        return BitpackedEvents(words, *(getattr(self, k).pin_memory() for k in self._TENSORS[1:]),
+                               self.max_count, self.skipped)
+
+
+def pack_events_bitpacked(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
+                          strict: bool = True) -> BitpackedEvents:
+    """Loader-side builder of the bit-packed wire layout from an upstream-layout `[B, M, 6]` CPU
+    tensor (`cmax_pack_events_host_bitpacked`, C++ / OpenMP).  Lossless for any float32 values."""
+    from . import cabi
+    import ctypes
+    lib = cabi.load()
+    cfg = _cfg_of(loss_or_cfg)
+    ev = events.detach().to(torch.float32).cpu().contiguous()
+    B, M, six = ev.shape
+    assert six == 6, "events must be [B, M, 6]"
+    _, nty, ntx, G = cabi.pack_layout(cfg)
+    F = G * nty * ntx * cfg.num_bins
+    npos = int(num_pos_events) if (cfg.polarity_aware_batching and num_pos_events is not None) else 0
+    fine = torch.empty((B, F + 1), dtype=torch.int32)
+    hdr = torch.zeros((B, F, 4), dtype=torch.int32)
+    rword = torch.empty((B, F + 1), dtype=torch.int32)
+    woff = torch.zeros(B + 1, dtype=torch.int64)
+    skipped = torch.zeros(2, dtype=torch.int64)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())             # noqa: E731
+    cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, None, 0, p(fine), p(hdr), p(rword),
+                                                   p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")
+    _check_binary_valid(int(skipped[1]), strict)
+    words = torch.zeros(max(int(woff[-1]), 4), dtype=torch.int32)
+    cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, p(words), words.numel(), p(fine), p(hdr),
+                                                   p(rword), p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")
+    return BitpackedEvents(words, fine, hdr, rword, woff, max(int(fine[:, -1].max()) if B else 0, 1), skipped)
+
+
+def expand_bitpacked(bp: BitpackedEvents, loss_or_cfg, out: Optional[PackedEvents] = None) -> PackedEvents:
+    """Device: bit-packed wire layout -> `PackedEvents` (one kernel, on the current stream)."""
+    from . import cabi
+    lib = cabi.load()
+    cfg = _cfg_of(loss_or_cfg)
+    if not bp.is_cuda:
+        raise RuntimeError("expand_bitpacked needs CUDA tensors (BitpackedEvents.to(device) first)")
+    dev = bp.device
+    B = bp.fine_start.shape[0]
+    _, nty, ntx, G = cabi.pack_layout(cfg)
+    Mp = int(bp.max_count)
+    if out is None or out.records.shape[0] != B or out.records.shape[1] < Mp:
+        out = PackedEvents(torch.empty((B, Mp, 4), dtype=torch.float32, device=dev),
+                           torch.empty((B, G * nty * ntx + 1), dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        cabi.check(lib.cmax_expand_bitpacked(cfg, cabi.ptr(bp.words), cabi.ptr(bp.fine_start), cabi.ptr(bp.run_hdr),
+                                             cabi.ptr(bp.run_word), cabi.ptr(bp.word_off), B, out.records.shape[1],
+                                             cabi.ptr(out.records), cabi.ptr(out.seg_start), cabi.stream_ptr(dev)),
+                   "cmax_expand_bitpacked")
+    return out
+
+
+def expand_wire(wire, loss_or_cfg, out: Optional[PackedEvents] = None) -> PackedEvents:
+    """`expand_compact` or `expand_bitpacked`, by the type of the wire layout."""
+    if isinstance(wire, BitpackedEvents):
+        return expand_bitpacked(wire, loss_or_cfg, out)
+    return expand_compact(wire, loss_or_cfg, out)
+
+
 class CompactUploader:
-    """Double-buffered H2D staging of `CompactEvents` batches: ONE copy of `12 B x events` (plus two
-    small tables) from pinned memory on a copy stream; `wait(slot)` makes the consumer's stream wait
-    for it and returns the device `PackedEvents` rebuilt there by the expand kernel."""
+    """Double-buffered H2D staging of `CompactEvents` / `BitpackedEvents` batches: ONE big copy of the
+    event payload (12 B x events, or the ~8 B x events bit stream) plus a few small tables from pinned
+    memory on a copy stream; `wait(slot)` makes the consumer's stream wait for it and returns the
+    device `PackedEvents` rebuilt there by the expand kernel."""
 
     def __init__(self, device, loss_or_cfg, n_buffers: int = 2):
         self.device = torch.device(device)
         self.cfg = _cfg_of(loss_or_cfg)
         self.stream = torch.cuda.Stream(self.device)
         self.n = n_buffers
-        self.wire = [None] * n_buffers           # device CompactEvents buffers (capacity may exceed use)
+        self.wire = [None] * n_buffers           # device wire-layout buffers (capacity may exceed use)
         self.out = [None] * n_buffers            # device PackedEvents buffers
         self.ready = [torch.cuda.Event() for _ in range(n_buffers)]
         self.free = [torch.cuda.Event() for _ in range(n_buffers)]
         self.turn = 0
         self.bytes_last = 0
-        self.issue_ms_last = 0.0                 # host time spent issuing the copies + the kernel
+        self.issue_ms_last = 0.0                 # host time spent issuing the copies
         for ev in self.free:
             ev.record(torch.cuda.current_stream(self.device))
 
-    def upload(self, compact: CompactEvents):
+    @staticmethod
+    def _payload(wire):
+        """(name of the big tensor, rows in use, names of the small tables)"""
+        if isinstance(wire, BitpackedEvents):
+            return "words", int(wire.word_off[-1]), ("fine_start", "run_hdr", "run_word", "word_off")
+        return "coords", int(wire.sample_off[-1]), ("fine_start", "sample_off")
+
+    def upload(self, wire_host):
         import time
-        assert compact.coords.is_pinned() and compact.fine_start.is_pinned() and compact.sample_off.is_pinned()
+        big, used, small = self._payload(wire_host)
+        assert getattr(wire_host, big).is_pinned() and all(getattr(wire_host, k).is_pinned() for k in small)
         t0 = time.perf_counter()
         slot = self.turn
         self.turn = (self.turn + 1) % self.n
-        T = int(compact.sample_off[-1])
+        src = getattr(wire_host, big)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.free[slot])
             w = self.wire[slot]
-            if w is None or w.coords.shape[0] < max(T, 1) or w.fine_start.shape != compact.fine_start.shape:
-                cap = max(int(T * 1.25), 1)
-                w = CompactEvents(torch.empty((cap, 3), dtype=torch.float32, device=self.device),
-                                  torch.empty(compact.fine_start.shape, dtype=torch.int32, device=self.device),
-                                  torch.empty(compact.sample_off.shape, dtype=torch.int64, device=self.device), 0)
+            if (w is None or type(w) is not type(wire_host) or getattr(w, big).shape[0] < max(used, 1)
+                    or w.fine_start.shape != wire_host.fine_start.shape):
+                cap = (max(int(used * 1.25), 4),) + tuple(src.shape[1:])
+                tensors = {big: torch.empty(cap, dtype=src.dtype, device=self.device)}
+                for k in small:
+                    t = getattr(wire_host, k)
+                    tensors[k] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                w = type(wire_host)(**tensors, max_count=0)
                 self.wire[slot] = w
-            if T:
-                w.coords[:T].copy_(compact.coords[:T], non_blocking=True)       # the one big copy
-            w.fine_start.copy_(compact.fine_start, non_blocking=True)
-            w.sample_off.copy_(compact.sample_off, non_blocking=True)
-            w.max_count = compact.max_count
-            self.bytes_last = T * 12 + compact.fine_start.numel() * 4 + compact.sample_off.numel() * 8
+            nbytes = 0
+            if used:
+                getattr(w, big)[:used].copy_(src[:used], non_blocking=True)       # the one big copy
+                nbytes += used * src[0].numel() * src.element_size()
+            for k in small:
+                getattr(w, k).copy_(getattr(wire_host, k), non_blocking=True)
+                nbytes += getattr(wire_host, k).numel() * getattr(wire_host, k).element_size()
+            w.max_count = wire_host.max_count
+            self.bytes_last = nbytes
             self.ready[slot].record(self.stream)
         self.issue_ms_last = (time.perf_counter() - t0) * 1e3
         return w, slot
@@ -522,7 +636,7 @@ class CompactUploader:
         stream = stream or torch.cuda.current_stream(self.device)
         stream.wait_event(self.ready[slot])
         with torch.cuda.stream(stream):
-            self.out[slot] = expand_compact(self.wire[slot], self.cfg, self.out[slot])
+            self.out[slot] = expand_wire(self.wire[slot], self.cfg, self.out[slot])
         return self.out[slot]
 
     def release(self, slot: int, stream=None):

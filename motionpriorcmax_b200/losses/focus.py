@@ -204,9 +204,10 @@ class FocusLoss(base.TrajectoryLossBase):
         # training (a backward will follow): the forward also emits dL/dIWE from its image pass
         cfg = self._cfg_train if (trajectories.requires_grad and torch.is_grad_enabled()) else self._cfg
         if hasattr(events, 'fine_start'):
-            # io.CompactEvents (12-byte wire layout): rebuild the packed records on the device first
+            # io.CompactEvents / io.BitpackedEvents (wire layouts): rebuild the packed records on the
+            # device first
             from .. import io as _io
-            events = _io.expand_compact(events, self)
+            events = _io.expand_wire(events, self)
         if hasattr(events, 'seg_start'):
             # io.PackedEvents: the loader-side tile-binned layout; the polarity split is part of it
             out = _CmaxLossFunction.apply(trajectories, times, events.records, cfg, 0,

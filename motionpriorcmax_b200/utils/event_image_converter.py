@@ -29,6 +29,8 @@ class EventImageConverter(object):
     # -- upstream :45-74 ------------------------------------------------------
     def create_iwe(self, events: torch.Tensor, method: str = "bilinear_vote", sigma: int = 1,
                    weight=1.0) -> torch.Tensor:
+        if hasattr(events, "run_hdr"):                       # io.BitpackedEvents: decode to records first
+            raise NotImplementedError("pass io.expand_bitpacked(events, loss) (a PackedEvents) to the imager")
         if hasattr(events, "fine_start") or hasattr(events, "seg_start"):
             # loader-side layouts (io.CompactEvents / io.PackedEvents) as `batch['events']`: what the
             # image-logging callback hands over (upstream src/utils/logging.py:76-79).  Rendered from

@@ -1,0 +1,9 @@
+python -m pytest tests/test_packed_events.py -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 20 --warmup 5 --no-cpu --no-train > gpurun_out/r2_b18.json 2>gpurun_out/r2_b18.err; tail -3 gpurun_out/r2_b18.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/r2_b18.json"))
+e=d["e2e"]
+print("value %.2f G %.3f ms | e2e %.2f G %.3f ms bytes %d copy %.2f ms %.1f GB/s | cg %.3f | compact12 %.3f ms %d B | ref %.3f | pack %.3f s"%(d["value"]/1e9,d["ms_per_step"],e["value"]/1e9,e["ms_per_step"],e["h2d_bytes_per_step"],e["copy_alone_ms"],e["h2d_GBps_per_rank_copy_alone"],e["with_coeff_grid_from_host"]["ms_per_step_rank0"],e["compact_12B_layout"]["ms_per_step_rank0"],e["compact_12B_layout"]["h2d_bytes_per_step"],d["e2e_reference_layout"]["ms_per_step"],e["host_pack_s_per_batch_rank0"]))
+print({k:round(v,3) for k,v in d["roofline"]["stage_ms_per_launch"].items()})
+PY

@@ -218,6 +218,63 @@ def test_compact_host_packer_layout_contract(s, pab):
         assert fs[-1] == int((key >= 0).sum())
 
 
+def _decode_bitpacked(bp):
+    """numpy restatement of the bit-packed layout contract (include/cmax_b200.h): uint32 [T, 3]."""
+    words = bp.words.numpy().view(np.uint32)
+    hdr = bp.run_hdr.numpy().view(np.uint32)
+    out = []
+    for b in range(bp.fine_start.shape[0]):
+        w = words[int(bp.word_off[b]):]
+        fs = bp.fine_start[b].numpy()
+        for f in np.nonzero(np.diff(fs))[0]:
+            wd = [int(hdr[b, f, 3] >> (8 * c)) & 255 for c in range(3)]
+            for k in range(int(fs[f + 1] - fs[f])):
+                bit = int(bp.run_word[b, f]) * 32 + k * sum(wd)
+                row = []
+                for c in range(3):
+                    v = 0
+                    if wd[c]:
+                        wi, sh = bit >> 5, bit & 31
+                        v = ((int(w[wi]) | (int(w[wi + 1]) << 32)) >> sh) & ((1 << wd[c]) - 1)
+                    row.append((int(hdr[b, f, c]) + v) & 0xffffffff)
+                    bit += wd[c]
+                out.append(row)
+    return np.array(out, np.uint32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("s,pab", [(4, True), (3, False)])
+def test_bitpacked_host_packer_is_lossless(s, pab):
+    """cmax_pack_events_host_bitpacked: decoding the bit stream with a numpy restatement of the
+    contract gives back the compact layout's (y, x, t) BIT FOR BIT - also for values that make a run
+    wide (-0.0, tiny and huge t, NaN t, coordinates a few ulp around cell edges) - in fewer bytes."""
+    from motionpriorcmax_b200 import io, synthetic
+    H, W, nb = 120, 150, 9
+    d = dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(H, W), num_bins=nb, lut_superpixel_size=s,
+             num_knn=2, polarity_aware_batching=pab)
+    cfg = _cfg(d)
+    ev, npos = synthetic.make_event_batch(3, [9000, 0, 4000], H, W, nb, pab, seed=6)
+    ev = ev.clone()
+    ev[0, 0, 0] = -0.0
+    ev[0, 1, 2] = float("nan")
+    ev[0, 2, 2] = 1e-30
+    ev[0, 3, 2] = -3.0
+    ev[0, 4, 2] = 1e30
+    rng = np.random.default_rng(4)
+    k = 300
+    edge = (rng.integers(0, H // s, k) * s).astype(np.float32)
+    ev[2, :k, 0] = torch.as_tensor(edge + rng.choice(np.array([0, 1e-6, 1e-5], np.float32), k))
+    c = io.pack_events_compact(ev, npos, cfg)
+    b = io.pack_events_bitpacked(ev, npos, cfg)
+    assert torch.equal(c.fine_start, b.fine_start) and c.skipped.tolist() == b.skipped.tolist()
+    T = int(c.sample_off[-1])
+    assert np.array_equal(_decode_bitpacked(b), c.coords.numpy().view(np.uint32)[:T])
+    assert b.max_count == c.max_count
+    # a realistic window: well under 12 bytes per event
+    ev2, npos2 = synthetic.make_event_batch(1, [300_000], 480, 640, 15, True, seed=2)
+    big = io.pack_events_bitpacked(ev2, npos2, _cfg(dict(synthetic.DSEC_LOSS_CONFIG)))
+    assert big.nbytes() < 9.5 * 300_000
+
+
 def _cuda():
     assert torch.cuda.is_available(), "these tests need a GPU (run with -m gpu on a B200)"
     return torch.device("cuda:0")
@@ -239,6 +296,8 @@ def _run(cfg, traj, times, events, npos, mode, deterministic=False):
         batch = {"events": io.pack_events(ev.to(dev), npos if npos >= 0 else None, L)}
     elif mode == "compact":      # 12-byte wire layout, expanded on the device inside calc
         batch = {"events": io.pack_events_compact(ev, npos if npos >= 0 else None, L).to(dev)}
+    elif mode == "bitpacked":    # ~8-byte lossless wire layout (bit-pattern deltas per run)
+        batch = {"events": io.pack_events_bitpacked(ev, npos if npos >= 0 else None, L).to(dev)}
     else:
         batch = {"events": io.pack_events_host(ev, npos if npos >= 0 else None, L).to(dev)}
     loss, log, misc = L.calc(t, torch.as_tensor(times, device=dev), batch, return_flow_lut=True)
@@ -251,7 +310,7 @@ def _run(cfg, traj, times, events, npos, mode, deterministic=False):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", LOSS_CASES)
-@pytest.mark.parametrize("mode", ["packed_dev", "packed_host", "compact"])
+@pytest.mark.parametrize("mode", ["packed_dev", "packed_host", "compact", "bitpacked"])
 def test_packed_matches_reference_golden(name, mode):
     from test_gpu_parity import _assert_grad_close
     c = load_case(name)
@@ -270,7 +329,7 @@ def test_packed_deterministic_is_bit_identical_to_unpacked(name):
     kernels must reproduce the unpacked kernels bit for bit (IWE, loss, gradients)."""
     c = load_case(name)
     a = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], "plain", True)
-    for mode in ("packed_dev", "packed_host", "compact"):
+    for mode in ("packed_dev", "packed_host", "compact", "bitpacked"):
         b = _run(c["cfg"], c["trajectories"], c["times"], c["events"], c["num_pos_events"], mode, True)
         assert a["loss"] == b["loss"] and a["focus"] == b["focus"]
         assert np.array_equal(a["iwes"], b["iwes"])
@@ -305,7 +364,17 @@ def test_compact_expands_to_the_host_packed_layout():
         b = up.wait(slot)
         torch.cuda.synchronize()
         assert up.bytes_last == 12 * int(comp.sample_off[-1]) + comp.fine_start.numel() * 4 + comp.sample_off.numel() * 8
-        for got in (a, b):
+        bp = io.pack_events_bitpacked(ev, npos, cfg)
+        c = io.expand_bitpacked(bp.to(dev), cfg)
+        up2 = io.CompactUploader(dev, cfg)
+        _, slot2 = up2.upload(bp.pin_memory())
+        d2 = up2.wait(slot2)
+        torch.cuda.synchronize()
+        assert up2.bytes_last == bp.nbytes() - (bp.words.numel() - int(bp.word_off[-1])) * 4
+        nrec = host.records.shape[1]                     # bit for bit the records of the 12-byte layout
+        for bb, cnt in enumerate(host.seg_start[:, -1].tolist()):
+            assert torch.equal(c.records[bb, :cnt].view(torch.int32), a.records[bb, :cnt].view(torch.int32))
+        for got in (a, b, c, d2):
             assert torch.equal(host.seg_start, got.seg_start.cpu())
             assert _segments(host, layout) == _segments(
                 io.PackedEvents(got.records[:, :host.records.shape[1]], got.seg_start), layout)
