@@ -150,7 +150,10 @@ int cmax_pack_events_host_compact(const CmaxConfig *cfg, const float *events_hos
                                   int64_t *skipped_host);
 int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_t *fine_start,
                         const int64_t *sample_off, int64_t B, int64_t records_stride,
-                        float *records_out, int32_t *seg_start_out, void *stream);
+                        float *records_out, int32_t *seg_start_out, int32_t *scratch, void *stream);
+/* int32 elements of DEVICE scratch both expand calls need (the run of the first record of every
+ * block of 256 records, filled by a tiny kernel before the expansion). */
+int64_t cmax_expand_scratch_ints(const CmaxConfig *cfg, int64_t B, int64_t records_stride);
 
 /* Bit-packed wire layout: the runs of the compact layout, every run stored as fixed-width records of
  * bit-pattern deltas (inside one (group, tile, bin) run y, x and t vary little, and the IEEE bit
@@ -171,7 +174,8 @@ int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const float *events_h
                                     int64_t *word_off_host, int64_t *skipped_host);
 int cmax_expand_bitpacked(const CmaxConfig *cfg, const uint32_t *words, const int32_t *fine_start,
                           const uint32_t *run_hdr, const int32_t *run_word, const int64_t *word_off, int64_t B,
-                          int64_t records_stride, float *records_out, int32_t *seg_start_out, void *stream);
+                          int64_t records_stride, float *records_out, int32_t *seg_start_out, int32_t *scratch,
+                          void *stream);
 
 /* cmax_forward / cmax_backward on the packed layout: same outputs, same workspace
  * (cmax_workspace_bytes(cfg, B, M, n) with the M of `records`).  The event stage accumulates

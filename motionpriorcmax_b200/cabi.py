@@ -28,7 +28,7 @@ EXPORTS = (
     "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
     "cmax_backward_accumulate", "cmax_backward_finish", "cmax_pack_events_host",
     "cmax_pack_events_host_compact", "cmax_expand_compact",
-    "cmax_pack_events_host_bitpacked", "cmax_expand_bitpacked",
+    "cmax_pack_events_host_bitpacked", "cmax_expand_bitpacked", "cmax_expand_scratch_ints",
 )
 
 
@@ -81,9 +81,11 @@ def load():
     lib.cmax_pack_events_host_bitpacked.argtypes = [POINTER(CmaxConfig), P, c_int64, c_int64, c_int64, P, c_int64,
                                                     P, P, P, P, P]
     lib.cmax_expand_bitpacked.restype = c_int32
-    lib.cmax_expand_bitpacked.argtypes = [POINTER(CmaxConfig), P, P, P, P, P, c_int64, c_int64, P, P, P]
+    lib.cmax_expand_bitpacked.argtypes = [POINTER(CmaxConfig), P, P, P, P, P, c_int64, c_int64, P, P, P, P]
+    lib.cmax_expand_scratch_ints.restype = c_int64
+    lib.cmax_expand_scratch_ints.argtypes = [POINTER(CmaxConfig), c_int64, c_int64]
     lib.cmax_expand_compact.restype = c_int32
-    lib.cmax_expand_compact.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, P, P, P]
+    lib.cmax_expand_compact.argtypes = [POINTER(CmaxConfig), P, P, P, c_int64, c_int64, P, P, P, P]
     lib.cmax_forward_packed.restype = c_int32
     lib.cmax_forward_packed.argtypes = [POINTER(CmaxConfig), P, P, P, P, c_int64, c_int64, c_int64,
                                         P, P, P, P, c_size_t, P]

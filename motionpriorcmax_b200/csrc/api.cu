@@ -566,39 +566,48 @@ int cmax_pack_events(const CmaxConfig *cfg, const float *events, int64_t B, int6
                               reinterpret_cast<long long *>(skipped_out), static_cast<cudaStream_t>(stream));
 }
 
+int64_t cmax_expand_scratch_ints(const CmaxConfig *cfg, int64_t B, int64_t records_stride)
+{
+    Geom g;
+    if (make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g) != CMAX_OK) return 0;
+    const int64_t span = records_stride > g.P * g.nt + 1 ? records_stride : g.P * g.nt + 1;
+    return B * ((span + 255) / 256);
+}
+
 int cmax_expand_compact(const CmaxConfig *cfg, const float *coords, const int32_t *fine_start,
                         const int64_t *sample_off, int64_t B, int64_t records_stride,
-                        float *records_out, int32_t *seg_start_out, void *stream)
+                        float *records_out, int32_t *seg_start_out, int32_t *scratch, void *stream)
 {
     DeviceGuard dev_guard(seg_start_out);
     Geom g;
     int rc = make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g);
     if (rc != CMAX_OK) return rc;
     if ((rc = pack_supported(g))) return rc;
-    if (!fine_start || !sample_off || !seg_start_out || (records_stride > 0 && (!coords || !records_out)))
+    if (!fine_start || !sample_off || !seg_start_out || !scratch || (records_stride > 0 && (!coords || !records_out)))
         return CMAX_ERR_BAD_SHAPE;
     if (((uintptr_t)records_out & 15u)) return CMAX_ERR_WORKSPACE;
     return launch_expand_compact(g, coords, fine_start, reinterpret_cast<const long long *>(sample_off),
-                                 records_stride, reinterpret_cast<float4 *>(records_out), seg_start_out,
+                                 records_stride, reinterpret_cast<float4 *>(records_out), seg_start_out, scratch,
                                  static_cast<cudaStream_t>(stream));
 }
 
 int cmax_expand_bitpacked(const CmaxConfig *cfg, const uint32_t *words, const int32_t *fine_start,
                           const uint32_t *run_hdr, const int32_t *run_word, const int64_t *word_off, int64_t B,
-                          int64_t records_stride, float *records_out, int32_t *seg_start_out, void *stream)
+                          int64_t records_stride, float *records_out, int32_t *seg_start_out, int32_t *scratch,
+                          void *stream)
 {
     DeviceGuard dev_guard(seg_start_out);
     Geom g;
     int rc = make_geom(cfg, B, records_stride, cfg ? cfg->num_knn : 1, 0, &g);
     if (rc != CMAX_OK) return rc;
     if ((rc = pack_supported(g))) return rc;
-    if (!fine_start || !run_hdr || !run_word || !word_off || !seg_start_out ||
+    if (!fine_start || !run_hdr || !run_word || !word_off || !seg_start_out || !scratch ||
         (records_stride > 0 && (!words || !records_out)))
         return CMAX_ERR_BAD_SHAPE;
     if (((uintptr_t)records_out & 15u) || ((uintptr_t)run_hdr & 15u)) return CMAX_ERR_WORKSPACE;
     return launch_expand_bitpacked(g, words, fine_start, run_hdr, run_word,
                                    reinterpret_cast<const long long *>(word_off), records_stride,
-                                   reinterpret_cast<float4 *>(records_out), seg_start_out,
+                                   reinterpret_cast<float4 *>(records_out), seg_start_out, scratch,
                                    static_cast<cudaStream_t>(stream));
 }
 

@@ -77,10 +77,10 @@ int launch_pack_events(const Geom &g, const float *events, float4 *records, int 
                        int *scratch, long long *skipped, cudaStream_t st);
 int launch_expand_compact(const Geom &g, const float *coords, const int *fine_start,
                           const long long *sample_off, int64_t Mp, float4 *records, int *seg_start,
-                          cudaStream_t st);
+                          int *block_run, cudaStream_t st);
 int launch_expand_bitpacked(const Geom &g, const unsigned *words, const int *fine_start, const unsigned *run_hdr,
                             const int *run_word, const long long *word_off, int64_t Mp, float4 *records,
-                            int *seg_start, cudaStream_t st);
+                            int *seg_start, int *block_run, cudaStream_t st);
 int launch_event_forward_packed(const Geom &g, const Layout &L, const float4 *records,
                                 const int *seg_start, const float *times, char *ws, cudaStream_t st);
 int launch_event_backward_packed(const Geom &g, const Layout &L, const float4 *records,
@@ -210,7 +210,22 @@ __device__ __forceinline__ float approx_sqrt(float x)
 
 // Python-style float floor division, the arithmetic of torch's `//` on float tensors
 // (c10 div_floor_floating) used by focus.py:186-187.
+__device__ __forceinline__ float floordiv_f32_generic(float a, float b);
+
+// Fast path of the same function for a divisor that is a power of two (every shipped config:
+// lut_superpixel_size = 4): fmod is exact, a - mod is an exact multiple of b and the quotient an
+// integer, so the whole recipe below reduces to floor(a / b) - and a * (1 / b) is exact as long as
+// it does not underflow (|a| >= 1e-30; smaller magnitudes take the generic recipe).  Saves two
+// ~40-instruction fmodf sequences per event.
 __device__ __forceinline__ float floordiv_f32(float a, float b)
+{
+    const unsigned bb = __float_as_uint(b);
+    if (b > 0.0f && (bb & 0x007fffffu) == 0u && (fabsf(a) >= 1e-30f) && fabsf(a) < 1e30f)
+        return floorf(__fmul_rn(a, __frcp_rn(b)));
+    return floordiv_f32_generic(a, b);
+}
+
+__device__ __forceinline__ float floordiv_f32_generic(float a, float b)
 {
     float mod = fmodf(a, b);
     float div = __fdiv_rn(__fsub_rn(a, mod), b);

@@ -450,6 +450,16 @@ def pack_events_compact(events: torch.Tensor, num_pos_events: Optional[int], los
     return CompactEvents(coords, fine, off, max(int(fine[:, -1].max()) if B else 0, 1), skipped)
 
 
+def _expand_scratch(out: PackedEvents, lib, cfg, B: int) -> torch.Tensor:
+    """Device scratch of the expand kernels, kept on the output object (reused with it)."""
+    need = int(lib.cmax_expand_scratch_ints(cfg, B, out.records.shape[1]))
+    sc = getattr(out, "_scratch", None)
+    if sc is None or sc.numel() < need or sc.device != out.records.device:
+        sc = torch.empty(max(need, 1), dtype=torch.int32, device=out.records.device)
+        out._scratch = sc
+    return sc
+
+
 def expand_compact(compact: CompactEvents, loss_or_cfg, out: Optional[PackedEvents] = None) -> PackedEvents:
     """Device: compact wire layout -> `PackedEvents` (one kernel, on the current stream)."""
     from . import cabi
@@ -464,10 +474,11 @@ def expand_compact(compact: CompactEvents, loss_or_cfg, out: Optional[PackedEven
     if out is None or out.records.shape[0] != B or out.records.shape[1] < Mp:
         out = PackedEvents(torch.empty((B, Mp, 4), dtype=torch.float32, device=dev),
                            torch.empty((B, G * nty * ntx + 1), dtype=torch.int32, device=dev))
+    scratch = _expand_scratch(out, lib, cfg, B)
     with torch.cuda.device(dev):
         cabi.check(lib.cmax_expand_compact(cfg, cabi.ptr(compact.coords), cabi.ptr(compact.fine_start),
                                            cabi.ptr(compact.sample_off), B, out.records.shape[1],
-                                           cabi.ptr(out.records), cabi.ptr(out.seg_start),
+                                           cabi.ptr(out.records), cabi.ptr(out.seg_start), cabi.ptr(scratch),
                                            cabi.stream_ptr(dev)), "cmax_expand_compact")
     return out
 
@@ -553,11 +564,12 @@ def expand_bitpacked(bp: BitpackedEvents, loss_or_cfg, out: Optional[PackedEvent
     if out is None or out.records.shape[0] != B or out.records.shape[1] < Mp:
         out = PackedEvents(torch.empty((B, Mp, 4), dtype=torch.float32, device=dev),
                            torch.empty((B, G * nty * ntx + 1), dtype=torch.int32, device=dev))
+    scratch = _expand_scratch(out, lib, cfg, B)
     with torch.cuda.device(dev):
         cabi.check(lib.cmax_expand_bitpacked(cfg, cabi.ptr(bp.words), cabi.ptr(bp.fine_start), cabi.ptr(bp.run_hdr),
                                              cabi.ptr(bp.run_word), cabi.ptr(bp.word_off), B, out.records.shape[1],
-                                             cabi.ptr(out.records), cabi.ptr(out.seg_start), cabi.stream_ptr(dev)),
-                   "cmax_expand_bitpacked")
+                                             cabi.ptr(out.records), cabi.ptr(out.seg_start), cabi.ptr(scratch),
+                                             cabi.stream_ptr(dev)), "cmax_expand_bitpacked")
     return out
 
 
