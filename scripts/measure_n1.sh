@@ -1,3 +1,4 @@
+# Round measurement on one GPU (gpurun -- "bash scripts/measure_n1.sh"): bench, reference arm, variants, sweep, ncu launch list.
 set -x
 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_n1.json 2> gpurun_out/r02_bench_reference_n1.err

@@ -1,3 +1,4 @@
+# Round measurement at N GPUs (usage: gpurun --gpus N -- "bash scripts/measure_ngpu.sh N"): bench, bench without NUMA binding, sweep.
 N=$1
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
 tail -2 gpurun_out/r02_bench_n$N.err
