@@ -235,6 +235,18 @@ int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_
 int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride,
                      int32_t H, int32_t W, int64_t *out, void *stream);
 
+/* The same two with the imager's outer_padding (event_image_converter.py:23-28, 339-343): H, W are
+ * the PADDED image sizes (image + 2 * pad), the integer corner of every event is shifted by
+ * (pad_y, pad_x) after the floor; fractional parts and weights are unchanged.  pad = 0 is the
+ * plain call. */
+int cmax_create_iwe_padded(const float *events, const float *weight, int64_t nb, int64_t M,
+                           int64_t row_stride, int32_t H, int32_t W, int32_t pad_y, int32_t pad_x,
+                           float sigma, float *out, float *scratch, int64_t *scratch_i64,
+                           int32_t deterministic, void *stream);
+int cmax_count_image_padded(const float *events, int64_t nb, int64_t M, int64_t row_stride,
+                            int32_t H, int32_t W, int32_t pad_y, int32_t pad_x, int64_t *out,
+                            void *stream);
+
 /* Test / inspection entry: the K nearest trajectories of every LUT cell exactly as cmax_forward
  * selects them (focus.py:128-137), ascending distance, lowest index first on ties.
  *   points [S, n, 2] (S independent slabs = B * nb);  ind_out [S, q, K] int32;
@@ -268,6 +280,11 @@ int cmax_trajectories_backward(const float *dtraj, const float *phi, int64_t B, 
 int cmax_voxel_grid(const float *x, const float *y, const float *t, const float *p, int64_t n,
                     int32_t C, int32_t H, int32_t W, int32_t norm_type, float *grid_out,
                     double *stats_scratch, void *stream);
+/* Second half of VoxelGrid.convert on an existing grid (utils.py:56-75), in place: optional
+ * quantile clipping |v| > thr -> sign(v) * thr with thr = *clip_threshold (DEVICE pointer, NULL =
+ * no clipping; the order statistic itself is the caller's), then the normalisation as above. */
+int cmax_voxel_normalize(float *grid, int32_t C, int32_t H, int32_t W, int32_t norm_type,
+                         const float *clip_threshold, double *stats_scratch, void *stream);
 
 /* Dense flow read-out, upstream dense_flow_from_traj (src/utils/flow.py:8-16): list_to_grid
  * (src/utils/trajectories.py:54-75) on the patch lattice, then torchvision BICUBIC antialias

@@ -19,11 +19,11 @@ FOCUS = {"gradient_magnitude": 0, "variance": 1}        # upstream src/utils/los
 
 EXPORTS = (
     "cmax_abi_version", "cmax_error_string", "cmax_workspace_bytes", "cmax_forward",
-    "cmax_backward", "cmax_create_iwe", "cmax_count_image", "cmax_knn_workspace_bytes",
+    "cmax_backward", "cmax_create_iwe", "cmax_count_image", "cmax_create_iwe_padded", "cmax_count_image_padded", "cmax_knn_workspace_bytes",
     "cmax_knn_indices", "cmax_trajectories_forward", "cmax_trajectories_backward",
     "cmax_atomic_microbench", "cmax_read_status", "cmax_stage_count", "cmax_stage_name",
     "cmax_stage_timing_enable", "cmax_stage_timing_read", "cmax_launch_count",
-    "cmax_last_worklist_count", "cmax_last_worklist_reasons", "cmax_voxel_grid", "cmax_dense_flow",
+    "cmax_last_worklist_count", "cmax_last_worklist_reasons", "cmax_voxel_grid", "cmax_voxel_normalize", "cmax_dense_flow",
     "cmax_pack_layout", "cmax_pack_events", "cmax_forward_packed", "cmax_backward_packed",
     "cmax_workspace_section", "cmax_forward_accumulate", "cmax_forward_finish",
     "cmax_backward_accumulate", "cmax_backward_finish", "cmax_pack_events_host",
@@ -112,6 +112,11 @@ def load():
                                     P, P, c_int32, P]
     lib.cmax_count_image.restype = c_int32
     lib.cmax_count_image.argtypes = [P, c_int64, c_int64, c_int64, c_int32, c_int32, P, P]
+    lib.cmax_create_iwe_padded.restype = c_int32
+    lib.cmax_create_iwe_padded.argtypes = [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                           c_float, P, P, P, c_int32, P]
+    lib.cmax_count_image_padded.restype = c_int32
+    lib.cmax_count_image_padded.argtypes = [P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, P]
     lib.cmax_knn_workspace_bytes.restype = c_size_t
     lib.cmax_knn_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int64, c_int64, c_int32]
     lib.cmax_knn_indices.restype = c_int32
@@ -125,6 +130,8 @@ def load():
                                                c_int32, c_int32, c_int32, P, P]
     lib.cmax_voxel_grid.restype = c_int32
     lib.cmax_voxel_grid.argtypes = [P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P]
+    lib.cmax_voxel_normalize.restype = c_int32
+    lib.cmax_voxel_normalize.argtypes = [P, c_int32, c_int32, c_int32, c_int32, P, P, P]
     lib.cmax_dense_flow.restype = c_int32
     lib.cmax_dense_flow.argtypes = [P, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P]
     lib.cmax_atomic_microbench.restype = c_int32

@@ -7,7 +7,8 @@
 namespace cmax {
 
 int launch_splat(int mode, const float *events, const float *weight, int64_t nb, int64_t M,
-                 int64_t stride, int H, int W, float *out, long long *out_i64, cudaStream_t st);
+                 int64_t stride, int H, int W, int ph, int pw, float *out, long long *out_i64,
+                 cudaStream_t st);
 int launch_blur(const float *raw, float *out, int64_t planes, int H, int W, float sigma,
                 cudaStream_t st);
 extern const int *g_last_work_count;
@@ -663,13 +664,16 @@ int cmax_backward_packed(const CmaxConfig *cfg, const float *trajectories, const
     return launch_lut_backward(g, L, trajectories, ws, dtraj_out, st);
 }
 
-int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_t M,
-                    int64_t row_stride, int32_t H, int32_t W, float sigma, float *out,
-                    float *scratch, int64_t *scratch_i64, int32_t deterministic, void *stream)
+int cmax_create_iwe_padded(const float *events, const float *weight, int64_t nb, int64_t M,
+                           int64_t row_stride, int32_t H, int32_t W, int32_t pad_y, int32_t pad_x,
+                           float sigma, float *out, float *scratch, int64_t *scratch_i64,
+                           int32_t deterministic, void *stream)
 {
     DeviceGuard dev_guard(out);
     if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
         return CMAX_ERR_BAD_SHAPE;
+    if (pad_y < 0 || pad_x < 0 || 2 * (int64_t)pad_y >= H || 2 * (int64_t)pad_x >= W)
+        return CMAX_ERR_BAD_SHAPE;                       // H, W are the padded sizes
     if (sigma > 0.0f && (!scratch || H < 2 || W < 2)) return CMAX_ERR_WORKSPACE;
     if (deterministic && !scratch_i64) return CMAX_ERR_WORKSPACE;
     if (nb > 65535) return CMAX_ERR_UNSUPPORTED;
@@ -680,28 +684,45 @@ int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_
     int rc;
     if (deterministic) {
         cudaMemsetAsync(scratch_i64, 0, sizeof(long long) * count, st);
-        if ((rc = launch_splat(1, events, weight, nb, M, row_stride, H, W, nullptr,
+        if ((rc = launch_splat(1, events, weight, nb, M, row_stride, H, W, pad_y, pad_x, nullptr,
                                reinterpret_cast<long long *>(scratch_i64), st))) return rc;
         if ((rc = launch_fix_to_float(reinterpret_cast<long long *>(scratch_i64), raw, count, st))) return rc;
     } else {
         cudaMemsetAsync(raw, 0, sizeof(float) * count, st);
-        if ((rc = launch_splat(0, events, weight, nb, M, row_stride, H, W, raw, nullptr, st))) return rc;
+        if ((rc = launch_splat(0, events, weight, nb, M, row_stride, H, W, pad_y, pad_x, raw, nullptr, st)))
+            return rc;
     }
     if (sigma > 0.0f) return launch_blur(raw, out, nb, H, W, sigma, st);
     return check_launch();
 }
 
-int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride, int32_t H,
-                     int32_t W, int64_t *out, void *stream)
+int cmax_create_iwe(const float *events, const float *weight, int64_t nb, int64_t M,
+                    int64_t row_stride, int32_t H, int32_t W, float sigma, float *out,
+                    float *scratch, int64_t *scratch_i64, int32_t deterministic, void *stream)
+{
+    return cmax_create_iwe_padded(events, weight, nb, M, row_stride, H, W, 0, 0, sigma, out, scratch,
+                                  scratch_i64, deterministic, stream);
+}
+
+int cmax_count_image_padded(const float *events, int64_t nb, int64_t M, int64_t row_stride, int32_t H,
+                            int32_t W, int32_t pad_y, int32_t pad_x, int64_t *out, void *stream)
 {
     DeviceGuard dev_guard(out);
     if (nb < 0 || M < 0 || row_stride < 2 || H < 1 || W < 1 || !out || (!events && M > 0))
         return CMAX_ERR_BAD_SHAPE;
+    if (pad_y < 0 || pad_x < 0 || 2 * (int64_t)pad_y >= H || 2 * (int64_t)pad_x >= W)
+        return CMAX_ERR_BAD_SHAPE;
     if (nb > 65535) return CMAX_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(out, 0, sizeof(long long) * nb * (int64_t)H * W, st);
-    return launch_splat(2, events, nullptr, nb, M, row_stride, H, W, nullptr,
+    return launch_splat(2, events, nullptr, nb, M, row_stride, H, W, pad_y, pad_x, nullptr,
                         reinterpret_cast<long long *>(out), st);
+}
+
+int cmax_count_image(const float *events, int64_t nb, int64_t M, int64_t row_stride, int32_t H,
+                     int32_t W, int64_t *out, void *stream)
+{
+    return cmax_count_image_padded(events, nb, M, row_stride, H, W, 0, 0, out, stream);
 }
 
 static int knn_only_geom(int32_t H, int32_t W, int32_t s, int64_t S, int64_t n, int32_t K, Geom *g)

@@ -18,8 +18,11 @@ namespace cmax {
 constexpr int kMaxCells = 24576;      // cell-list cells per slab (smem counters, 96 KB)
 constexpr int kMaxTref = 16;          // reference times handled by the gather kernels
 constexpr int kKnnBlock = 128;        // threads per KNN CTA (one LUT query per thread)
-constexpr int kKnnTileW = 16;         // KNN CTA = 16 x 8 queries
-constexpr int kKnnTileH = 8;
+#ifndef CMAX_KNN_TILE_W
+#define CMAX_KNN_TILE_W 16
+#endif
+constexpr int kKnnTileW = CMAX_KNN_TILE_W;         // KNN CTA = 16 x 8 queries
+constexpr int kKnnTileH = kKnnBlock / kKnnTileW;
 constexpr int kMaxKnn = 192;          // heap lives in shared memory: 8 B * K * 128 threads
 constexpr int kImgTile = 32;          // image-stage CTA tile (32 x 32 pixels, 256 threads)
 constexpr double kFixScale = 4294967296.0;   // 2^32: int64 fixed-point scale (deterministic mode)
@@ -278,6 +281,31 @@ __device__ __forceinline__ Corners vote_corners(float wy, float wx, int H, int W
     c.idx[1] = (y1ok && x0ok) ? (iy + 1) * W + ix : -1;       // (y1+1, x1)
     c.idx[2] = (y0ok && x1ok) ? iy * W + ix + 1 : -1;         // (y1,   x1+1)
     c.idx[3] = (y1ok && x1ok) ? (iy + 1) * W + ix + 1 : -1;   // (y1+1, x1+1)
+    return c;
+}
+
+// The imager's outer padding (event_image_converter.py:339-380): the integer corner is shifted by
+// (ph, pw) AFTER the floor, the fractional parts are those of the unshifted coordinate, and the
+// bounds are those of the padded image (H, W).  Shifting the float coordinate instead would round.
+__device__ __forceinline__ Corners vote_corners_padded(float wy, float wx, int H, int W, int ph, int pw)
+{
+    Corners c;
+    const float yf = floorf(__fadd_rn(wy, kVoteEps)), xf = floorf(__fadd_rn(wx, kVoteEps));
+    c.fy = __fsub_rn(wy, yf);
+    c.fx = __fsub_rn(wx, xf);
+    // |floor| < 2^23 keeps the shifted corner an exact float; anything larger is far outside
+    const bool sane = fabsf(yf) < 8388608.0f && fabsf(xf) < 8388608.0f;
+    const float y1 = yf + (float)ph, x1 = xf + (float)pw;
+    bool y0ok = sane && (y1 >= 0.0f) && (y1 < (float)H);
+    bool y1ok = sane && (y1 >= -1.0f) && (y1 < (float)(H - 1));
+    bool x0ok = sane && (x1 >= 0.0f) && (x1 < (float)W);
+    bool x1ok = sane && (x1 >= -1.0f) && (x1 < (float)(W - 1));
+    int iy = (y0ok || y1ok) ? (int)y1 : 0;
+    int ix = (x0ok || x1ok) ? (int)x1 : 0;
+    c.idx[0] = (y0ok && x0ok) ? iy * W + ix : -1;
+    c.idx[1] = (y1ok && x0ok) ? (iy + 1) * W + ix : -1;
+    c.idx[2] = (y0ok && x1ok) ? iy * W + ix + 1 : -1;
+    c.idx[3] = (y1ok && x1ok) ? (iy + 1) * W + ix + 1 : -1;
     return c;
 }
 

@@ -145,7 +145,8 @@ __global__ void dlut_finalize_kernel(const long long *__restrict__ acc, float *_
 template <int MODE>   // 0: float votes, 1: int64 fixed-point votes, 2: unit counts (int64)
 __global__ void __launch_bounds__(256)
 splat_kernel(const float *__restrict__ events, const float *__restrict__ weight, int64_t M,
-             int64_t stride, int H, int W, float *__restrict__ out, long long *__restrict__ out_i64)
+             int64_t stride, int H, int W, int ph, int pw, float *__restrict__ out,
+             long long *__restrict__ out_i64)
 {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t b = blockIdx.y;
@@ -153,7 +154,7 @@ splat_kernel(const float *__restrict__ events, const float *__restrict__ weight,
     const float *row = events + (b * M + m) * stride;
     const float wy = row[0], wx = row[1];
     const float w = weight ? weight[b * M + m] : 1.0f;
-    const Corners c = vote_corners(wy, wx, H, W);
+    const Corners c = (ph | pw) ? vote_corners_padded(wy, wx, H, W, ph, pw) : vote_corners(wy, wx, H, W);
     const int64_t base = b * (int64_t)H * W;
     if (MODE == 2) {
 #pragma unroll
@@ -181,17 +182,18 @@ splat_kernel(const float *__restrict__ events, const float *__restrict__ weight,
 }
 
 int launch_splat(int mode, const float *events, const float *weight, int64_t nb, int64_t M,
-                 int64_t stride, int H, int W, float *out, long long *out_i64, cudaStream_t st)
+                 int64_t stride, int H, int W, int ph, int pw, float *out, long long *out_i64,
+                 cudaStream_t st)
 {
     if (M == 0 || nb == 0) return CMAX_OK;
     dim3 grid((unsigned)((M + 255) / 256), (unsigned)nb);
     count_launch();
     if (mode == 0)
-        splat_kernel<0><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+        splat_kernel<0><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, ph, pw, out, out_i64);
     else if (mode == 1)
-        splat_kernel<1><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+        splat_kernel<1><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, ph, pw, out, out_i64);
     else
-        splat_kernel<2><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, out, out_i64);
+        splat_kernel<2><<<grid, 256, 0, st>>>(events, weight, M, stride, H, W, ph, pw, out, out_i64);
     return check_launch();
 }
 

@@ -1236,7 +1236,10 @@ lut_accumulate_multi_kernel(const float *__restrict__ traj, Geom g, const int *_
 // exceeds the staging capacity take gather_generic, the global-memory walk of the same lattice.
 // Stage B (lut_backward_assemble_kernel): one thread per (sample, trajectory) sums the bins in a
 // fixed order -> deterministic.
-constexpr int kBwdTileH = 8, kBwdTileW = 16;      // cell-list cells per CTA (measured: 16x16 / 288 threads
+#ifndef CMAX_BWD_TILE_W
+#define CMAX_BWD_TILE_W 16
+#endif
+constexpr int kBwdTileW = CMAX_BWD_TILE_W, kBwdTileH = 128 / kBwdTileW;      // cell-list cells per CTA (measured: 16x16 / 288 threads
 constexpr int kBwdBlock = 128;                    // and 160 / 192 threads per 8x16 tile are all slower)
 constexpr int kBwdWinCap = 1280;                  // staged LUT cells per CTA (incl. row padding)
 constexpr int kBwdMaxRows = 64;

@@ -104,9 +104,48 @@ voxel_normalize_kernel(float *__restrict__ grid, int64_t count, const double *__
     }
 }
 
+// quantile clipping (utils.py:56-60): |v| > thr -> sign(v) * thr; thr is read from device memory so
+// the caller's order statistic needs no host round trip
+__global__ void __launch_bounds__(256)
+voxel_clip_kernel(float *__restrict__ grid, int64_t count, const float *__restrict__ thr_ptr)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float thr = __ldg(thr_ptr), v = grid[i];
+    if (fabsf(v) > thr) grid[i] = __fmul_rn(v > 0.0f ? 1.0f : -1.0f, thr);
+}
+
+static int normalize_grid(float *grid, int64_t count, int norm_type, double *stats, cudaStream_t st)
+{
+    cudaMemsetAsync(stats, 0, sizeof(double) * 4, st);
+    const int blocks = 148 * 8;
+    voxel_stats_kernel<<<blocks, 256, 0, st>>>(grid, count, stats, 0);
+    if (norm_type == 1) voxel_stats_kernel<<<blocks, 256, 0, st>>>(grid, count, stats, 1);
+    voxel_normalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(grid, count, stats, norm_type);
+    count_launch(norm_type == 1 ? 3 : 2);
+    return check_launch();
+}
+
 }  // namespace cmax
 
 using namespace cmax;
+
+extern "C" int cmax_voxel_normalize(float *grid, int32_t C, int32_t H, int32_t W, int32_t norm_type,
+                                    const float *clip_threshold, double *stats_scratch, void *stream)
+{
+    cmax::DeviceGuard dev_guard(grid);
+    if (C < 1 || H < 1 || W < 1 || !grid) return CMAX_ERR_BAD_SHAPE;
+    if ((unsigned)norm_type > 2u) return CMAX_ERR_BAD_CONFIG;
+    if (norm_type != 0 && !stats_scratch) return CMAX_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t count = (int64_t)C * H * W;
+    if (clip_threshold) {
+        voxel_clip_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(grid, count, clip_threshold);
+        count_launch();
+    }
+    if (norm_type != 0) return normalize_grid(grid, count, norm_type, stats_scratch, st);
+    return check_launch();
+}
 
 extern "C" int cmax_voxel_grid(const float *x, const float *y, const float *t, const float *p,
                                int64_t n, int32_t C, int32_t H, int32_t W, int32_t norm_type,
@@ -124,13 +163,6 @@ extern "C" int cmax_voxel_grid(const float *x, const float *y, const float *t, c
         voxel_splat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, t, p, n, C, H, W, grid_out);
         count_launch();
     }
-    if (norm_type != 0) {
-        cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 4, st);
-        const int blocks = 148 * 8;
-        voxel_stats_kernel<<<blocks, 256, 0, st>>>(grid_out, count, stats_scratch, 0);
-        if (norm_type == 1) voxel_stats_kernel<<<blocks, 256, 0, st>>>(grid_out, count, stats_scratch, 1);
-        voxel_normalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(grid_out, count, stats_scratch, norm_type);
-        count_launch(norm_type == 1 ? 3 : 2);
-    }
+    if (norm_type != 0) return normalize_grid(grid_out, count, norm_type, stats_scratch, st);
     return check_launch();
 }

@@ -21,10 +21,23 @@ class EventImageConverter(object):
             self.outer_padding = (int(outer_padding), int(outer_padding))
         else:
             self.outer_padding = tuple(outer_padding)
-        if self.outer_padding != (0, 0):
-            raise NotImplementedError("outer_padding != 0 is not used on the loss path")
-        self.image_size = tuple(int(i) for i in image_size)
+        self.outer_padding = tuple(int(p) for p in self.outer_padding)
+        if min(self.outer_padding) < 0:
+            raise ValueError("outer_padding must be >= 0")
+        # upstream :28: the images this converter returns are the padded ones
+        self.image_size = tuple(int(i + p * 2) for i, p in zip(image_size, self.outer_padding))
         self.deterministic = bool(deterministic)
+
+    # -- upstream :30-43 (kept as it is there, including the single - not double - padding it adds) --
+    def update_property(self, image_size=None, outer_padding=None):
+        if image_size is not None:
+            self.image_size = image_size
+        if outer_padding is not None:
+            if isinstance(outer_padding, int):
+                self.outer_padding = (outer_padding, outer_padding)
+            else:
+                self.outer_padding = outer_padding
+        self.image_size = tuple(i + p for i, p in zip(self.image_size, self.outer_padding))
 
     # -- upstream :45-74 ------------------------------------------------------
     def create_iwe(self, events: torch.Tensor, method: str = "bilinear_vote", sigma: int = 1,
@@ -55,9 +68,9 @@ class EventImageConverter(object):
         if method == "bilinear_vote":
             return torch.squeeze(self._vote(events, weight, float(sigma)))
         if method == "polarity":
+            # upstream :156-163: boolean indexing flattens a batch, so batched events give ONE
+            # (positive, negative) image pair of all windows together - kept as it is there
             pos_flag = events[..., 3] > 0
-            if events.dim() != 2:
-                raise NotImplementedError("method='polarity' needs un-batched events")
             wt = isinstance(weight, torch.Tensor)
             pos = self._vote(events[pos_flag], weight[pos_flag] if wt else weight, float(sigma))
             neg = self._vote(events[~pos_flag], weight[~pos_flag] if wt else weight, float(sigma))
@@ -73,12 +86,13 @@ class EventImageConverter(object):
     def count_event_tensor(self, events: torch.Tensor) -> torch.Tensor:
         ev = self._prep(events)
         h, w = self.image_size
+        ph, pw = self.outer_padding
         nb, m, c = ev.shape
         out = torch.empty((nb, h, w), dtype=torch.int64, device=ev.device)
         lib = cabi.load()
         with torch.cuda.device(ev.device):
-            cabi.check(lib.cmax_count_image(cabi.ptr(ev), nb, m, c, h, w, cabi.ptr(out),
-                                            cabi.stream_ptr(ev.device)), "cmax_count_image")
+            cabi.check(lib.cmax_count_image_padded(cabi.ptr(ev), nb, m, c, h, w, ph, pw, cabi.ptr(out),
+                                                   cabi.stream_ptr(ev.device)), "cmax_count_image_padded")
         return out.squeeze()
 
     # ------------------------------------------------------------------------
@@ -136,11 +150,12 @@ class EventImageConverter(object):
         scratch64 = (torch.empty((nb, h, w), dtype=torch.int64, device=ev.device)
                      if self.deterministic else None)
         lib = cabi.load()
+        ph, pw = self.outer_padding
         with torch.cuda.device(ev.device):
-            rc = lib.cmax_create_iwe(cabi.ptr(ev), cabi.ptr(wt), nb, m, c, h, w, sigma, cabi.ptr(out),
-                                     cabi.ptr(scratch), cabi.ptr(scratch64), int(self.deterministic),
-                                     cabi.stream_ptr(ev.device))
-        cabi.check(rc, "cmax_create_iwe")
+            rc = lib.cmax_create_iwe_padded(cabi.ptr(ev), cabi.ptr(wt), nb, m, c, h, w, ph, pw, sigma,
+                                            cabi.ptr(out), cabi.ptr(scratch), cabi.ptr(scratch64),
+                                            int(self.deterministic), cabi.stream_ptr(ev.device))
+        cabi.check(rc, "cmax_create_iwe_padded")
         if sigma > 0:
             out = out[:, None]            # upstream blurs a [nb, 1, H, W] view, then squeezes
         return out

@@ -3,8 +3,9 @@
 Same constructor (``input_size=(C, H, W), norm_type, quantile``) and ``convert(events)`` with
 ``events = {'p', 't', 'x', 'y'}`` 1-D float tensors; the tensors must live on a CUDA device and
 the grid is built by ``cmax_voxel_grid`` (one streaming splat pass + the normalisation kernels)
-instead of eight masked ``put_`` passes on the CPU.  The rarely used quantile clipping
-(``quantile > 0``; ``dsec.yaml`` ships 0) needs a global order statistic and stays in torch.
+instead of eight masked ``put_`` passes on the CPU.  For the rarely used quantile clipping
+(``quantile > 0``; ``dsec.yaml`` ships 0) the order statistic is ``torch.quantile``; clipping and
+normalisation of the clipped grid are ``cmax_voxel_normalize``.
 """
 from __future__ import annotations
 
@@ -40,16 +41,12 @@ class VoxelGrid:
         rc = lib.cmax_voxel_grid(cabi.ptr(x), cabi.ptr(y), cabi.ptr(t), cabi.ptr(p), n, C, H, W, norm,
                                  cabi.ptr(grid), cabi.ptr(stats), cabi.stream_ptr(x.device))
         cabi.check(rc, "cmax_voxel_grid")
-        if self.quantile > 0:                      # upstream :56-60, then the normalisation in torch
-            thr = torch.quantile(grid.abs().view(-1), 1 - self.quantile)
-            grid = torch.where(grid.abs() > thr, grid.sign() * thr, grid)
-            if self.norm_type == 'mean_std':
-                mask = torch.nonzero(grid, as_tuple=True)
-                if mask[0].size()[0] > 0:
-                    mean, std = grid[mask].mean(), grid[mask].std()
-                    grid[mask] = (grid[mask] - mean) / std if std > 0 else grid[mask] - mean
-            elif self.norm_type == 'max':
-                mx = grid.abs().max()
-                if mx > 0:
-                    grid = grid / mx
+        if self.quantile > 0:
+            # upstream :56-60: clip to the (1 - q) quantile of |grid|, then normalise the clipped grid.
+            # The order statistic is torch's; clipping and normalisation run in the library on the
+            # device-resident threshold (no host round trip).
+            thr = torch.quantile(grid.abs().view(-1), 1 - self.quantile).reshape(1).contiguous()
+            rc = lib.cmax_voxel_normalize(cabi.ptr(grid), C, H, W, _NORM[self.norm_type], cabi.ptr(thr),
+                                          cabi.ptr(stats), cabi.stream_ptr(x.device))
+            cabi.check(rc, "cmax_voxel_normalize")
         return grid

@@ -309,18 +309,20 @@ def lut_cell_indices(events: np.ndarray, s: int):
     return it, iy, ix
 
 
-def vote_corners(yx: np.ndarray, image_shape):
+def vote_corners(yx: np.ndarray, image_shape, outer_padding=(0, 0)):
     """event_image_converter.py:354-380: f = floor(yx + 1e-6) in *float32*, corner linear
     indices (OOB -> 0) and in-bounds masks for the 4 corners in reference order
     (y1,x1), (y1+1,x1), (y1,x1+1), (y1+1,x1+1).  Returns (inds int64 [..., 4],
-    mask bool [..., 4], frac [..., 2] in yx's dtype)."""
+    mask bool [..., 4], frac [..., 2] in yx's dtype).  `image_shape` is the (padded) image the
+    votes land in; `outer_padding` (ph, pw) shifts the integer corner after the floor (:339-343)."""
     H, W = image_shape
+    ph, pw = outer_padding
     yx32 = np.asarray(yx, np.float32)
     with np.errstate(invalid="ignore"):
         fl = np.floor(yx32 + np.float32(1e-6))
     frac = np.asarray(yx) - fl.astype(np.asarray(yx).dtype)
     fl = np.where(np.isfinite(fl), fl, -(2.0 ** 40)).astype(np.int64)
-    y1, x1 = fl[..., 0], fl[..., 1]
+    y1, x1 = fl[..., 0] + ph, fl[..., 1] + pw
     inds = np.stack((x1 + y1 * W, x1 + (y1 + 1) * W, (x1 + 1) + y1 * W, (x1 + 1) + (y1 + 1) * W), -1)
     okx0, okx1 = (0 <= x1) & (x1 < W), (0 <= x1 + 1) & (x1 + 1 < W)
     oky0, oky1 = (0 <= y1) & (y1 < H), (0 <= y1 + 1) & (y1 + 1 < H)
@@ -328,13 +330,13 @@ def vote_corners(yx: np.ndarray, image_shape):
     return inds * mask, mask, frac
 
 
-def count_image(events_yx: np.ndarray, image_shape) -> np.ndarray:
+def count_image(events_yx: np.ndarray, image_shape, outer_padding=(0, 0)) -> np.ndarray:
     """event_image_converter.py:226-272 (count_event_tensor): 4 unit votes per event -> int64."""
     H, W = image_shape
     ev = np.asarray(events_yx)
     if ev.ndim == 2:
         ev = ev[None]
-    inds, mask, _ = vote_corners(ev[..., :2], image_shape)
+    inds, mask, _ = vote_corners(ev[..., :2], image_shape, outer_padding)
     out = np.zeros((ev.shape[0], H * W), np.int64)
     for b in range(ev.shape[0]):
         out[b] = np.bincount(inds[b].reshape(-1), weights=mask[b].reshape(-1).astype(np.float64),
@@ -342,7 +344,7 @@ def count_image(events_yx: np.ndarray, image_shape) -> np.ndarray:
     return out.reshape(ev.shape[0], H, W)
 
 
-def bilinear_vote(events_yx: np.ndarray, weight, image_shape, dtype=np.float32) -> np.ndarray:
+def bilinear_vote(events_yx: np.ndarray, weight, image_shape, dtype=np.float32, outer_padding=(0, 0)) -> np.ndarray:
     """event_image_converter.py:333-391 (bilinear_vote_tensor) -> raw IWE [nb, H, W]."""
     H, W = image_shape
     ev = np.asarray(events_yx)
@@ -350,7 +352,7 @@ def bilinear_vote(events_yx: np.ndarray, weight, image_shape, dtype=np.float32) 
         ev = ev[None]
     nb = ev.shape[0]
     yx = ev[..., :2].astype(dtype)
-    inds, mask, frac = vote_corners(yx, image_shape)
+    inds, mask, frac = vote_corners(yx, image_shape, outer_padding)
     fy, fx = frac[..., 0], frac[..., 1]
     w = np.broadcast_to(np.asarray(weight, dtype), fy.shape)
     one = dtype(1)
@@ -363,9 +365,9 @@ def bilinear_vote(events_yx: np.ndarray, weight, image_shape, dtype=np.float32) 
     return out.reshape(nb, H, W)
 
 
-def create_iwe(events, image_shape, weight=1.0, sigma=1, dtype=np.float32) -> np.ndarray:
-    """event_image_converter.py:45-74 with method='bilinear_vote' -> [nb, H, W]."""
-    img = bilinear_vote(events, weight, image_shape, dtype)
+def create_iwe(events, image_shape, weight=1.0, sigma=1, dtype=np.float32, outer_padding=(0, 0)) -> np.ndarray:
+    """event_image_converter.py:45-74 with method='bilinear_vote' -> [nb, H, W] (H, W = padded sizes)."""
+    img = bilinear_vote(events, weight, image_shape, dtype, outer_padding)
     return blur(img, sigma) if sigma > 0 else img
 
 

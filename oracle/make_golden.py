@@ -172,7 +172,8 @@ def build_imager_case():
     from src.utils import EventImageConverter
     torch.manual_seed(7)
     H, W = 20, 28
-    im = EventImageConverter((H, W))
+    PAD = (2, 3)
+    im, imp = EventImageConverter((H, W)), EventImageConverter((H, W), outer_padding=PAD)
     n = 900
     yx = torch.rand(2, n, 2) * torch.tensor([H + 6.0, W + 6.0]) - 3.0
     # exact integers, values a hair below integers, tiny negatives, the far corner
@@ -186,7 +187,14 @@ def build_imager_case():
         os.path.join(OUT, "imager.npz"), events=ev.numpy(), weight=wt.numpy(), shape=np.array([H, W]),
         iwe_sigma1=im.create_iwe(ev, method="bilinear_vote", sigma=1, weight=wt).numpy(),
         iwe_sigma0=im.create_iwe(ev, method="bilinear_vote", sigma=0, weight=wt).numpy(),
-        iwe_unit=im.create_iwe(ev, method="bilinear_vote", sigma=0).numpy())
+        iwe_unit=im.create_iwe(ev, method="bilinear_vote", sigma=0).numpy(),
+        # outer_padding (:23-28, 339-343): votes land in an image enlarged by 2 * pad
+        pad=np.array(PAD), iwe_pad_sigma0=imp.create_iwe(ev, method="bilinear_vote", sigma=0, weight=wt).numpy(),
+        iwe_pad_sigma1=imp.create_iwe(ev, method="bilinear_vote", sigma=1, weight=wt).numpy(),
+        # method='polarity' (:156-163): un-batched and batched (boolean indexing flattens the batch)
+        iwe_polarity_unbatched=im.create_iwe(ev[0], method="polarity", sigma=1, weight=wt[0]).numpy(),
+        iwe_polarity_batched=im.create_iwe(ev, method="polarity", sigma=0, weight=wt).numpy(),
+        iwe_polarity_batched_unit=im.create_iwe(ev, method="polarity", sigma=1).numpy())
     # NOTE: the reference's count_event_tensor (event_image_converter.py:226-272) cannot be
     # executed: it scatter_adds int64 votes into a float image and torch raises
     # "Expected self.dtype to be equal to src.dtype".  The count image is therefore pinned

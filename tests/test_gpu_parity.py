@@ -116,6 +116,21 @@ def test_imager_matches_reference_golden():
         assert b.shape == z["iwe_sigma0"].shape and rel_err(b, z["iwe_sigma0"]) < TOL
         u = im.create_iwe(ev, method="bilinear_vote", sigma=0).cpu().numpy()
         assert rel_err(u, z["iwe_unit"]) < TOL
+        # method='polarity' (un-batched, batched = flattened, unit weight) against the reference
+        for name, args in (("iwe_polarity_unbatched", dict(events=ev[0], sigma=1, weight=wt[0])),
+                           ("iwe_polarity_batched", dict(events=ev, sigma=0, weight=wt)),
+                           ("iwe_polarity_batched_unit", dict(events=ev, sigma=1))):
+            p = im.create_iwe(method="polarity", **args).cpu().numpy()
+            assert p.shape == z[name].shape and rel_err(p, z[name]) < TOL, name
+        # outer_padding: the reference's padded images
+        pad = tuple(int(v) for v in z["pad"])
+        imp = EventImageConverter((H, W), outer_padding=pad, deterministic=det)
+        assert imp.image_size == (H + 2 * pad[0], W + 2 * pad[1])
+        for name, sg in (("iwe_pad_sigma0", 0), ("iwe_pad_sigma1", 1)):
+            p = imp.create_iwe(ev, method="bilinear_vote", sigma=sg, weight=wt).cpu().numpy()
+            assert p.shape == z[name].shape and rel_err(p, z[name]) < TOL, name
+    cntp = imp.create_image_from_events_tensor(ev, method="count").cpu().numpy()
+    assert np.array_equal(cntp, fo.count_image(z["events"], imp.image_size, pad))
     # integer work: count image bit-exact against the oracle's restatement of the shared
     # index / mask arithmetic (the reference's own count_event_tensor raises, see make_golden.py)
     cnt = EventImageConverter((H, W)).create_image_from_events_tensor(ev, method="count").cpu().numpy()

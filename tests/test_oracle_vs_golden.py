@@ -73,6 +73,18 @@ def test_imager_matches_reference():
     _, mask, _ = fo.vote_corners(ev[..., :2], (H, W))
     assert cnt.dtype == np.int64 and cnt.sum() == mask.sum()
     assert ((cnt > 0) >= (unit > 0)).all()
+    # outer_padding: the padded image, corners shifted after the floor
+    pad = tuple(int(v) for v in z["pad"])
+    HP, WP = H + 2 * pad[0], W + 2 * pad[1]
+    assert rel_err(fo.create_iwe(ev, (HP, WP), wt, sigma=0, outer_padding=pad), z["iwe_pad_sigma0"]) < 1e-6
+    assert rel_err(fo.create_iwe(ev, (HP, WP), wt, sigma=1, outer_padding=pad), z["iwe_pad_sigma1"]) < 1e-6
+    # method='polarity': positive / negative events voted separately; a batch is flattened
+    pos = ev[..., 3] > 0
+    for name, e_, w_, sg in (("iwe_polarity_unbatched", ev[0], wt[0], 1), ("iwe_polarity_batched", ev, wt, 0)):
+        p_ = e_[..., 3] > 0
+        got = np.stack((fo.create_iwe(e_[p_], (H, W), w_[p_], sigma=sg)[0],
+                        fo.create_iwe(e_[~p_], (H, W), w_[~p_], sigma=sg)[0]))
+        assert rel_err(got, z[name]) < 1e-6
 
 
 def test_integer_semantics_of_float32_floor():
