@@ -275,13 +275,32 @@ __device__ __forceinline__ Query make_query(int c, const Geom &g)
 // ---------------------------------------------------------------------------------------------
 // 2. fast path
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 1152;    // staged records per CTA (points + 3 sentinels per window row)
-constexpr int kListCap = 24;       // boundary candidates kept per thread
+// (compile-time knobs: scripts/build_variant.sh NAME -DCMAX_KNN_...=v builds a variant library)
+#ifndef CMAX_KNN_STAGE_CAP
+#define CMAX_KNN_STAGE_CAP 1152
+#endif
+#ifndef CMAX_KNN_LIST_CAP
+#define CMAX_KNN_LIST_CAP 24
+#endif
+#ifndef CMAX_KNN_CTAS
+#define CMAX_KNN_CTAS 8
+#endif
+#ifndef CMAX_KNN_GUESS_LO
+#define CMAX_KNN_GUESS_LO 0.84f
+#endif
+#ifndef CMAX_KNN_GUESS_HI
+#define CMAX_KNN_GUESS_HI 1.15f
+#endif
+constexpr int kStageCap = CMAX_KNN_STAGE_CAP;    // staged records per CTA (points + 3 sentinels per window row)
+constexpr int kListCap = CMAX_KNN_LIST_CAP;      // boundary candidates kept per thread
 constexpr int kRowPad = 3;         // sentinel records after every staged window row
 constexpr int kWinRows = kKnnTileH + 2 * 10;
 constexpr int kWinCols = kKnnTileW + 2 * 10;
-constexpr float kGuessLo = 0.82f;  // bracket around the previous bin's K-th key
-constexpr float kGuessHi = 1.22f;
+// bracket around the previous bin's K-th key.  Measured (DSEC batch 14): most fast-path misses are
+// FULL LISTS, not keys outside the bracket - [0.82, 1.22] gives 12.7 k misses and knn 0.900 ms,
+// [0.84, 1.15] 12.5 k and 0.854 ms (shorter lists to slice), [0.88, 1.15] 40 k, [0.80, 1.25] 22 k
+constexpr float kGuessLo = CMAX_KNN_GUESS_LO;
+constexpr float kGuessHi = CMAX_KNN_GUESS_HI;
 
 // bucket 0: d < lo; buckets 1..7: seven slices of [lo, hi); 8: d >= hi (not counted)
 __device__ __forceinline__ int bucket_of(float d, float lo, float invw)
@@ -332,7 +351,7 @@ __device__ __forceinline__ void classify(float d, float lo, float hi, float2 f, 
 //                everything below the bracket and lists the few candidates inside it.  A miss
 //                (bracket wrong, list full) sends the cell to the work list - never a wrong answer.
 template <bool L1D, bool FUSED, bool GUESS>
-__global__ void __launch_bounds__(kKnnBlock, 8)
+__global__ void __launch_bounds__(kKnnBlock, CMAX_KNN_CTAS)
 knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_start,
                 const float4 *__restrict__ recs_all, const int *__restrict__ sorted_j_all,
                 float *__restrict__ lut, float *__restrict__ lut_copy, float *__restrict__ tau,

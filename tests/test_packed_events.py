@@ -275,6 +275,42 @@ def test_bitpacked_host_packer_is_lossless(s, pab):
     assert big.nbytes() < 9.5 * 300_000
 
 
+def test_bitpacked_round_trip_on_arbitrary_bit_patterns():
+    """Property test (hypothesis): any float32 bit pattern in t (NaN payloads, infinities, denormals,
+    either sign) and any in-range coordinate mantissa survives pack -> decode bit for bit, whatever
+    the run widths come out as (0 ... 32 bits per field)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    from motionpriorcmax_b200 import io, synthetic
+    H, W, nb, s = 16, 24, 3, 4
+    cfg = _cfg(dict(synthetic.DSEC_LOSS_CONFIG, image_shape=(H, W), num_bins=nb, lut_superpixel_size=s,
+                    num_knn=2, polarity_aware_batching=True))
+
+    @settings(max_examples=40, deadline=None)
+    @given(hnp.arrays(np.uint32, (37,), elements=st.integers(0, 2 ** 32 - 1)),
+           hnp.arrays(np.uint32, (37, 2), elements=st.integers(0, 2 ** 23 - 1)),
+           st.integers(0, 37))
+    def check(tbits, mant, npos):
+        n = len(tbits)
+        ev = np.zeros((1, n, 6), np.float32)
+        # coordinates in [0, H) x [0, W): integer part from the high mantissa bits, arbitrary low bits
+        ev[0, :, 0] = (mant[:, 0].astype(np.float64) / 2 ** 23 * H).astype(np.float32).clip(0, np.nextafter(np.float32(H), np.float32(0)))
+        ev[0, :, 1] = (mant[:, 1].astype(np.float64) / 2 ** 23 * W).astype(np.float32).clip(0, np.nextafter(np.float32(W), np.float32(0)))
+        ev[0, :, 2] = tbits.view(np.float32)
+        ev[0, :, 3] = 1.0
+        ev[0, :, 4] = (np.arange(n) % nb).astype(np.float32)
+        ev[0, :, 5] = 1.0
+        e = torch.from_numpy(ev)
+        c = io.pack_events_compact(e, npos, cfg)
+        b = io.pack_events_bitpacked(e, npos, cfg)
+        T = int(c.sample_off[-1])
+        assert T == n and torch.equal(c.fine_start, b.fine_start)
+        assert np.array_equal(_decode_bitpacked(b), c.coords.numpy().view(np.uint32)[:T])
+
+    check()
+
+
 def _cuda():
     assert torch.cuda.is_available(), "these tests need a GPU (run with -m gpu on a B200)"
     return torch.device("cuda:0")
@@ -355,6 +391,10 @@ def test_compact_expands_to_the_host_packed_layout():
         rng = np.random.default_rng(2)
         edge = (rng.integers(0, H // s, k) * s).astype(np.float32)
         ev[0, :k, 0] = torch.as_tensor(edge + rng.choice(np.array([-2e-6, -1e-6, 0, 1e-6, 1e-5], np.float32), k)).clamp_(0)
+        # arbitrary float32 bit patterns in t (NaN payloads, infinities, denormals, both signs): the
+        # device decoder must hand back every one of them (runs up to 32 bits wide)
+        tb = rng.integers(0, 2 ** 32, 2000, dtype=np.uint64).astype(np.uint32)
+        ev[1, 100:2100, 2] = torch.from_numpy(tb.view(np.float32).copy())
         layout = cabi.pack_layout(cfg)
         host = io.pack_events_native(ev, npos, cfg)
         comp = io.pack_events_compact(ev, npos, cfg)
