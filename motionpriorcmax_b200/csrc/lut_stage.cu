@@ -285,6 +285,12 @@ __device__ __forceinline__ Query make_query(int c, const Geom &g)
 #ifndef CMAX_KNN_CTAS
 #define CMAX_KNN_CTAS 8
 #endif
+#ifndef CMAX_KNN_EST_LO
+#define CMAX_KNN_EST_LO 0.45f      // first bin: bracket around the density estimate of the K-th key
+#endif
+#ifndef CMAX_KNN_EST_HI
+#define CMAX_KNN_EST_HI 1.7f
+#endif
 #ifndef CMAX_KNN_GUESS_LO
 #define CMAX_KNN_GUESS_LO 0.84f
 #endif
@@ -622,8 +628,8 @@ knn_fast_kernel(Geom g, int bin, int chain_len, const int *__restrict__ cell_sta
             const float area = (float)((e_r1 - e_r0 + 1) * (e_c1 - e_c0)) * g.cs * g.cs;
             float est = (float)g.K * area / (3.14159265f * (float)max(nwin, 1));
             if (L1D) est = sqrtf(est * 1.5707963f);        // l1 ball of radius t has area 2 t^2
-            float lo = 0.45f * est;
-            float hi = fminf(1.7f * est, bnd);
+            float lo = CMAX_KNN_EST_LO * est;
+            float hi = fminf(CMAX_KNN_EST_HI * est, bnd);
             miss = 1;
             for (int attempt = 0; attempt < 5 && hi > lo; ++attempt) {
                 const float invw = 7.0f / (hi - lo);
