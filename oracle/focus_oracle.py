@@ -203,7 +203,8 @@ def knn_bruteforce(points: np.ndarray, grid: np.ndarray, K: int, norm: str = "l2
         dist = np.empty((B, nb, q, K), np.float32)
         rc = lib.oracle_knn_bruteforce(points.ctypes.data, grid.ctypes.data, B * nb, n, q, K,
                                        1 if norm == "l1" else 0, ind.ctypes.data,
-                                       dist.ctypes.data, os.cpu_count() or 1)
+                                       dist.ctypes.data,
+                                       int(os.environ.get("ORACLE_KNN_THREADS", os.cpu_count() or 1)))
         assert rc == 0
         return ind, dist
     ind = np.empty((B, nb, q, K), np.int64)
