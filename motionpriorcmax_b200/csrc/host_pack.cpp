@@ -15,7 +15,7 @@
 namespace {
 
 // torch's `//` on float32 (c10::div_floor_floating), the arithmetic of focus.py:186-187
-inline float floordiv_f32(float a, float b)
+inline float floordiv_f32_generic(float a, float b)
 {
     const float mod = fmodf(a, b);
     float div = (a - mod) / b;
@@ -30,8 +30,21 @@ inline float floordiv_f32(float a, float b)
     return fd;
 }
 
+// Same fast path as the device code (cmax_common.cuh): for a power-of-two divisor fmod is exact,
+// a - mod an exact multiple of b, and the recipe reduces to floor(a / b); a * (1 / b) is exact as
+// long as it does not underflow.  Two fmodf calls per row were most of the packer's time.
+inline float floordiv_f32(float a, float b)
+{
+    uint32_t bb;
+    memcpy(&bb, &b, 4);
+    const float aa = fabsf(a);
+    if (b > 0.0f && (bb & 0x007fffffu) == 0u && aa >= 1e-30f && aa < 1e30f) return floorf(a * (1.0f / b));
+    return floordiv_f32_generic(a, b);
+}
+
 struct HostLayout {
     int s, nb, Hq, Wq, ct, nty, ntx, nt, G;
+    int ct_shift;      // log2(ct) when ct is a power of two (every shipped config), else -1
 };
 
 bool host_layout(const CmaxConfig *c, HostLayout *L)
@@ -47,6 +60,9 @@ bool host_layout(const CmaxConfig *c, HostLayout *L)
     L->ntx = out[2];
     L->nt = L->nty * L->ntx;
     L->G = out[3];
+    L->ct_shift = -1;
+    for (int sh = 0; sh < 16; ++sh)
+        if ((1 << sh) == L->ct) L->ct_shift = sh;
     return true;
 }
 
@@ -63,6 +79,7 @@ inline int row_key(const float *row, int64_t m, int64_t npos, const HostLayout &
     const int it = (int)ft, iy = (int)fy, ix = (int)fx;
     const int grp = (L.G == 2 && m >= npos) ? 1 : 0;
     *meta = ((uint32_t)it << 24) | ((uint32_t)iy << 12) | (uint32_t)ix;
+    if (L.ct_shift >= 0) return grp * L.nt + (iy >> L.ct_shift) * L.ntx + (ix >> L.ct_shift);
     return grp * L.nt + (iy / L.ct) * L.ntx + ix / L.ct;
 }
 
@@ -241,52 +258,58 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
         int32_t *seg = fine_start_host + b * (int64_t)(nkeys + 1);
         uint32_t *hdr = run_hdr_host + b * (int64_t)nkeys * 4;
         int32_t *rw = run_word_host + b * (int64_t)(nkeys + 1);
-        std::vector<int32_t> key((size_t)M);
-        std::vector<int32_t> cursor((size_t)nkeys + 1, 0);
+        // pass A: run of every row, event count and per-field minimum / maximum bit pattern of every
+        // run (the run tables are a few hundred KB: they stay in cache while the rows stream by)
+        std::vector<int32_t> key(fill ? (size_t)M : 0);
+        std::vector<int32_t> count((size_t)nkeys, 0);
+        std::vector<uint32_t> mn((size_t)nkeys * 3, 0xffffffffu), mx((size_t)nkeys * 3, 0u);
         for (int64_t m = 0; m < M; ++m) {
             uint32_t mw = 0;
-            int k = row_key(ev + m * 6, m, num_pos_events, L, &mw);
+            const float *row = ev + m * 6;
+            int k = row_key(row, m, num_pos_events, L, &mw);
             if (k >= 0) {
                 k = k * L.nb + (int)(mw >> 24);
-                ++cursor[(size_t)k + 1];
-                if (ev[m * 6 + 5] != 1.0f) ++odd;
+                ++count[(size_t)k];
+                if (row[5] != 1.0f) ++odd;
+                uint32_t v[3];
+                memcpy(v, row, 12);
+                for (int c = 0; c < 3; ++c) {
+                    if (v[c] < mn[(size_t)k * 3 + c]) mn[(size_t)k * 3 + c] = v[c];
+                    if (v[c] > mx[(size_t)k * 3 + c]) mx[(size_t)k * 3 + c] = v[c];
+                }
             } else if (k == -2) {
                 ++dropped;
-                if (ev[m * 6 + 5] != 1.0f) ++odd;
+                if (row[5] != 1.0f) ++odd;
             }
-            key[(size_t)m] = k;
+            if (fill) key[(size_t)m] = k;
         }
-        for (int k = 0; k < nkeys; ++k) cursor[(size_t)k + 1] += cursor[(size_t)k];
-        memcpy(seg, cursor.data(), sizeof(int32_t) * (size_t)(nkeys + 1));
-        // stable gather of the kept rows into run order (bit patterns of y, x, t)
-        const int32_t total = cursor[(size_t)nkeys];
-        std::vector<uint32_t> rows((size_t)total * 3);
-        for (int64_t m = 0; m < M; ++m) {
-            const int k = key[(size_t)m];
-            if (k < 0) continue;
-            uint32_t *dst = rows.data() + (size_t)cursor[(size_t)k]++ * 3;
-            memcpy(dst, ev + m * 6, 12);
-        }
-        // per run: minima, widths, first word
-        auto bitlen = [](uint32_t v) { int n = 0; while (v) { ++n; v >>= 1; } return n; };
+        auto bitlen = [](uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; };
         int64_t word = 0;
+        int32_t rows_before = 0;
+        std::vector<uint64_t> bitpos(fill ? (size_t)nkeys : 0);          // next free bit of every run
         for (int k = 0; k < nkeys; ++k) {
-            const int32_t a = seg[k], e = seg[k + 1];
-            uint32_t mn[3] = {0u, 0u, 0u}, mx[3] = {0u, 0u, 0u};
-            for (int32_t i = a; i < e; ++i)
-                for (int c = 0; c < 3; ++c) {
-                    const uint32_t v = rows[(size_t)i * 3 + c];
-                    if (i == a || v < mn[c]) mn[c] = v;
-                    if (i == a || v > mx[c]) mx[c] = v;
-                }
-            const int wy = bitlen(mx[0] - mn[0]), wx = bitlen(mx[1] - mn[1]), wt = bitlen(mx[2] - mn[2]);
-            hdr[k * 4 + 0] = mn[0];
-            hdr[k * 4 + 1] = mn[1];
-            hdr[k * 4 + 2] = mn[2];
+            const int32_t n = count[(size_t)k];
+            int wy = 0, wx = 0, wt = 0;
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u;
+            if (n > 0) {
+                m0 = mn[(size_t)k * 3];
+                m1 = mn[(size_t)k * 3 + 1];
+                m2 = mn[(size_t)k * 3 + 2];
+                wy = bitlen(mx[(size_t)k * 3] - m0);
+                wx = bitlen(mx[(size_t)k * 3 + 1] - m1);
+                wt = bitlen(mx[(size_t)k * 3 + 2] - m2);
+            }
+            seg[k] = rows_before;
+            rows_before += n;
+            hdr[k * 4 + 0] = m0;
+            hdr[k * 4 + 1] = m1;
+            hdr[k * 4 + 2] = m2;
             hdr[k * 4 + 3] = (uint32_t)wy | ((uint32_t)wx << 8) | ((uint32_t)wt << 16);
             rw[k] = (int32_t)word;
-            word += ((int64_t)(e - a) * (wy + wx + wt) + 31) / 32;
+            if (fill) bitpos[(size_t)k] = (uint64_t)word * 32u;
+            word += ((int64_t)n * (wy + wx + wt) + 31) / 32;
         }
+        seg[nkeys] = rows_before;
         rw[nkeys] = (int32_t)word;
         if (word + 2 > (int64_t)INT32_MAX) {
 #pragma omp critical
@@ -294,24 +317,33 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
             continue;
         }
         if (fill) {
+            // pass B: every kept row goes straight to the next free bits of its run (rows are
+            // visited in their original order, so the order inside a run is the original one)
+            if (word_off_host[b] + word + 2 > word_off_host[b + 1]) {          // tables from another batch
+#pragma omp critical
+                rc = CMAX_ERR_BAD_SHAPE;
+                continue;
+            }
             uint32_t *out = words_host + word_off_host[b];
             memset(out, 0, sizeof(uint32_t) * (size_t)(word + 2));
-            for (int k = 0; k < nkeys; ++k) {
-                const int32_t a = seg[k], e = seg[k + 1];
+            for (int64_t m = 0; m < M; ++m) {
+                const int k = key[(size_t)m];
+                if (k < 0) continue;
                 const uint32_t wv = hdr[k * 4 + 3];
-                const int w3[3] = {(int)(wv & 255u), (int)((wv >> 8) & 255u), (int)((wv >> 16) & 255u)};
-                uint64_t bit = (uint64_t)rw[k] * 32u;
-                for (int32_t i = a; i < e; ++i)
-                    for (int c = 0; c < 3; ++c) {
-                        const int w = w3[c];
-                        if (w == 0) continue;
-                        const uint64_t v = (uint64_t)(rows[(size_t)i * 3 + c] - hdr[k * 4 + c]);
-                        const uint64_t wi = bit >> 5;
-                        const int sh = (int)(bit & 31u);
-                        out[wi] |= (uint32_t)(v << sh);
-                        if (sh + w > 32) out[wi + 1] |= (uint32_t)(v >> (32 - sh));
-                        bit += (uint64_t)w;
-                    }
+                uint32_t v[3];
+                memcpy(v, ev + m * 6, 12);
+                uint64_t bit = bitpos[(size_t)k];
+                for (int c = 0; c < 3; ++c) {
+                    const int w = (int)((wv >> (8 * c)) & 255u);
+                    if (w == 0) continue;
+                    const uint64_t d = (uint64_t)(v[c] - hdr[k * 4 + c]);
+                    const uint64_t wi = bit >> 5;
+                    const int sh = (int)(bit & 31u);
+                    out[wi] |= (uint32_t)(d << sh);
+                    if (sh + w > 32) out[wi + 1] |= (uint32_t)(d >> (32 - sh));
+                    bit += (uint64_t)w;
+                }
+                bitpos[(size_t)k] = bit;
             }
         }
     }

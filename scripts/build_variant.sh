@@ -12,7 +12,7 @@ flags="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 for s in api lut_stage event_stage tile_stage image_stage voxel_stage flow_stage; do
   nvcc $flags "$@" -c $csrc/$s.cu -o $out/$s.o &
 done
-g++ -O3 -std=c++17 -fPIC -fopenmp -c $csrc/host_pack.cpp -o $out/host_pack.o
+g++ -O3 -msse4.1 -std=c++17 -fPIC -fopenmp -c $csrc/host_pack.cpp -o $out/host_pack.o
 wait
 nvcc -shared -o $out/libcmax_b200.so $out/*.o -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart shared -lgomp
 rm $out/*.o
