@@ -165,7 +165,10 @@ int64_t cmax_expand_scratch_ints(const CmaxConfig *cfg, int64_t B, int64_t recor
  *   run_hdr  [B, F, 4] uint32 (F = G * NT * nb): min patterns of y, x, t and wy | wx << 8 | wt << 16;
  *   run_word [B, F + 1] int32: first word of every run inside its window's stream (runs are word
  *            aligned); fine_start [B, F + 1] as in the compact layout.
- * cmax_pack_events_host_bitpacked (HOST pointers; first call with words_host = NULL for the sizes),
+ * cmax_pack_events_host_bitpacked (HOST pointers): words_host = NULL fills only the tables (word_off =
+ * the sizes); with words_host it fills tables and streams in the same call and returns
+ * CMAX_ERR_BAD_SHAPE (tables filled in) when words_capacity is too small - B * (3 * M + F + 2) words
+ * always suffice,
  * cmax_expand_bitpacked (DEVICE pointers): decodes into the packed layout, bit for bit the records
  * cmax_expand_compact produces. */
 int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const float *events_host, int64_t B, int64_t M,

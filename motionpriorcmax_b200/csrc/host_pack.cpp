@@ -231,8 +231,10 @@ extern "C" int cmax_pack_events_host_compact(const CmaxConfig *cfg, const float 
 //            (int64 [B + 1]); the stream of a window ends with two zero words of slack so that the
 //            decoder may always read three words per field window
 //   fine_start as in the compact layout (event counts per run)
-// Two calls like the compact packer: words_host = NULL fills fine_start / run_hdr / run_word /
-// word_off (sizes), the second call writes the stream.
+// words_host = NULL: only the tables (fine_start / run_hdr / run_word / word_off = the sizes).
+// words_host != NULL: tables AND streams in the same call; CMAX_ERR_BAD_SHAPE (tables and word_off
+// filled in) when words_capacity is too small - so either two calls with an exact buffer, or one
+// call with a buffer of B * (3 * M + F + 2) words, which always suffices.
 extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const float *events_host, int64_t B,
                                                int64_t M, int64_t num_pos_events, uint32_t *words_host,
                                                int64_t words_capacity, int32_t *fine_start_host,
@@ -250,17 +252,21 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
     const int nkeys = L.G * L.nt * L.nb;
     int64_t dropped = 0, odd = 0;
     const bool fill = words_host != nullptr;
-    if (fill && word_off_host[B] > words_capacity) return CMAX_ERR_BAD_SHAPE;
     int rc = CMAX_OK;
+    // phase 1 (parallel over the windows): run of every row, counts, per-run minima / widths, the
+    // words every window needs; phase 2 after the prefix over the windows: the bit streams.
+    std::vector<std::vector<int32_t>> keys((size_t)B);
+    std::vector<std::vector<uint64_t>> bitpos((size_t)B);                 // next free bit of every run
+    std::vector<int64_t> win_words((size_t)B, 0);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : dropped, odd)
     for (int64_t b = 0; b < B; ++b) {
         const float *ev = events_host + b * M * 6;
         int32_t *seg = fine_start_host + b * (int64_t)(nkeys + 1);
         uint32_t *hdr = run_hdr_host + b * (int64_t)nkeys * 4;
         int32_t *rw = run_word_host + b * (int64_t)(nkeys + 1);
-        // pass A: run of every row, event count and per-field minimum / maximum bit pattern of every
-        // run (the run tables are a few hundred KB: they stay in cache while the rows stream by)
-        std::vector<int32_t> key(fill ? (size_t)M : 0);
+        // (the run tables are a few hundred KB: they stay in cache while the rows stream by)
+        std::vector<int32_t> &key = keys[(size_t)b];
+        if (fill) key.resize((size_t)M);
         std::vector<int32_t> count((size_t)nkeys, 0);
         std::vector<uint32_t> mn((size_t)nkeys * 3, 0xffffffffu), mx((size_t)nkeys * 3, 0u);
         for (int64_t m = 0; m < M; ++m) {
@@ -286,7 +292,7 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
         auto bitlen = [](uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; };
         int64_t word = 0;
         int32_t rows_before = 0;
-        std::vector<uint64_t> bitpos(fill ? (size_t)nkeys : 0);          // next free bit of every run
+        if (fill) bitpos[(size_t)b].resize((size_t)nkeys);
         for (int k = 0; k < nkeys; ++k) {
             const int32_t n = count[(size_t)k];
             int wy = 0, wx = 0, wt = 0;
@@ -306,33 +312,38 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
             hdr[k * 4 + 2] = m2;
             hdr[k * 4 + 3] = (uint32_t)wy | ((uint32_t)wx << 8) | ((uint32_t)wt << 16);
             rw[k] = (int32_t)word;
-            if (fill) bitpos[(size_t)k] = (uint64_t)word * 32u;
+            if (fill) bitpos[(size_t)b][(size_t)k] = (uint64_t)word * 32u;
             word += ((int64_t)n * (wy + wx + wt) + 31) / 32;
         }
         seg[nkeys] = rows_before;
-        rw[nkeys] = (int32_t)word;
-        if (word + 2 > (int64_t)INT32_MAX) {
-#pragma omp critical
-            rc = CMAX_ERR_UNSUPPORTED;
-            continue;
-        }
-        if (fill) {
-            // pass B: every kept row goes straight to the next free bits of its run (rows are
-            // visited in their original order, so the order inside a run is the original one)
-            if (word_off_host[b] + word + 2 > word_off_host[b + 1]) {          // tables from another batch
-#pragma omp critical
-                rc = CMAX_ERR_BAD_SHAPE;
-                continue;
-            }
+        rw[nkeys] = (int32_t)(word < (int64_t)INT32_MAX ? word : (int64_t)INT32_MAX);
+        win_words[(size_t)b] = word;
+    }
+    // window offsets (two slack words each): an output of every call
+    word_off_host[0] = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        if (win_words[(size_t)b] + 2 > (int64_t)INT32_MAX) rc = CMAX_ERR_UNSUPPORTED;
+        word_off_host[b + 1] = word_off_host[b] + win_words[(size_t)b] + 2;
+    }
+    if (rc == CMAX_OK && fill && word_off_host[B] > words_capacity) rc = CMAX_ERR_BAD_SHAPE;   // sizes are filled in
+    if (rc == CMAX_OK && fill) {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; ++b) {
+            // every kept row goes straight to the next free bits of its run (rows are visited in
+            // their original order, so the order inside a run is the original one)
+            const float *ev = events_host + b * M * 6;
+            const uint32_t *hdr = run_hdr_host + b * (int64_t)nkeys * 4;
+            const std::vector<int32_t> &key = keys[(size_t)b];
+            std::vector<uint64_t> &bp = bitpos[(size_t)b];
             uint32_t *out = words_host + word_off_host[b];
-            memset(out, 0, sizeof(uint32_t) * (size_t)(word + 2));
+            memset(out, 0, sizeof(uint32_t) * (size_t)(win_words[(size_t)b] + 2));
             for (int64_t m = 0; m < M; ++m) {
                 const int k = key[(size_t)m];
                 if (k < 0) continue;
                 const uint32_t wv = hdr[k * 4 + 3];
                 uint32_t v[3];
                 memcpy(v, ev + m * 6, 12);
-                uint64_t bit = bitpos[(size_t)k];
+                uint64_t bit = bp[(size_t)k];
                 for (int c = 0; c < 3; ++c) {
                     const int w = (int)((wv >> (8 * c)) & 255u);
                     if (w == 0) continue;
@@ -343,14 +354,9 @@ extern "C" int cmax_pack_events_host_bitpacked(const CmaxConfig *cfg, const floa
                     if (sh + w > 32) out[wi + 1] |= (uint32_t)(d >> (32 - sh));
                     bit += (uint64_t)w;
                 }
-                bitpos[(size_t)k] = bit;
+                bp[(size_t)k] = bit;
             }
         }
-    }
-    if (!fill) {                                     // first call: window offsets (two slack words each)
-        word_off_host[0] = 0;
-        for (int64_t b = 0; b < B; ++b)
-            word_off_host[b + 1] = word_off_host[b] + run_word_host[b * (int64_t)(nkeys + 1) + nkeys] + 2;
     }
     if (skipped_host) {
         skipped_host[0] = dropped;

@@ -541,12 +541,16 @@ def pack_events_bitpacked(events: torch.Tensor, num_pos_events: Optional[int], l
     woff = torch.zeros(B + 1, dtype=torch.int64)
     skipped = torch.zeros(2, dtype=torch.int64)
     p = lambda t: ctypes.c_void_p(t.data_ptr())             # noqa: E731
-    cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, None, 0, p(fine), p(hdr), p(rword),
-                                                   p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")
-    _check_binary_valid(int(skipped[1]), strict)
-    words = torch.zeros(max(int(woff[-1]), 4), dtype=torch.int32)
-    cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, p(words), words.numel(), p(fine), p(hdr),
+    # one call: tables and streams together, into a buffer that always suffices (3 words per row +
+    # one alignment word per run + the slack; untouched pages of it are never committed), then the
+    # used part is copied out - cheaper than a sizing call, which repeats the pass over the rows
+    cap = max(B * (3 * M + F + 2), 4)
+    scratch = torch.empty(cap, dtype=torch.int32)
+    cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, p(scratch), cap, p(fine), p(hdr),
                                                    p(rword), p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")
+    _check_binary_valid(int(skipped[1]), strict)
+    words = scratch[:max(int(woff[-1]), 4)].clone()
+    del scratch
     return BitpackedEvents(words, fine, hdr, rword, woff, max(int(fine[:, -1].max()) if B else 0, 1), skipped)
 
 
