@@ -11,6 +11,10 @@ behind `cmax_pack_events_host`.  `FocusLoss.calc` accepts the packed batch uncha
         batch['events'] = batch['events'].to(device, non_blocking=True)
         loss, log, misc = loss_calculator.calc(trajectories, times, batch)
 
+`layout='bitpacked'` (or `'compact'`) hands out the wire layouts instead: a third of the bytes of the
+padded tensor cross PCIe, `calc` decodes them on the device (`io.CompactUploader` pipelines the
+copies of consecutive batches, see `bench.py`'s end-to-end leg).
+
     python examples/packed_collate.py        # self-check on synthetic windows
 """
 import os
@@ -26,10 +30,16 @@ from motionpriorcmax_b200 import cabi, io as cio, synthetic      # noqa: E402
 class PackedCollate:
     """Wraps the upstream collate function; picklable, so it works with worker processes."""
 
-    def __init__(self, loss_config: dict, upstream_collate=None, pin: bool = False):
+    PACKERS = {"packed": "pack_events_native",       # 16-byte records, ready for the kernels
+               "compact": "pack_events_compact",     # 12-byte wire layout, expanded on the device
+               "bitpacked": "pack_events_bitpacked"}  # lossless ~8-byte wire layout (least PCIe traffic)
+
+    def __init__(self, loss_config: dict, upstream_collate=None, pin: bool = False, layout: str = "packed"):
         self.loss_config = dict(loss_config)
         self.upstream_collate = upstream_collate
         self.pin = pin
+        self.layout = layout
+        assert layout in self.PACKERS
         self._cfg = None
 
     def _config(self):
@@ -42,7 +52,8 @@ class PackedCollate:
 
     def __call__(self, samples):
         batch = self.upstream_collate(samples) if self.upstream_collate else samples
-        packed = cio.pack_events_native(batch["events"], batch.get("num_pos_events"), self._config())
+        pack = getattr(cio, self.PACKERS[self.layout])
+        packed = pack(batch["events"], batch.get("num_pos_events"), self._config())
         batch["events"] = packed.pin_memory() if self.pin else packed
         return batch
 
@@ -73,6 +84,10 @@ def main():
     print(f"packed {n_valid} valid events of a [{ev.shape[0]}, {ev.shape[1]}, 6] batch "
           f"({ev.numel() * 4 / 1e6:.0f} MB) into {pk.records[:, :].numel() * 4 / 1e6:.0f} MB "
           f"+ {pk.seg_start.numel() * 4 / 1e3:.0f} KB of segment offsets in {dt * 1e3:.0f} ms")
+    t0 = time.perf_counter()
+    bp = PackedCollate(cfg, layout="bitpacked")({"events": ev, "num_pos_events": npos})["events"]
+    print(f"bit-packed wire layout: {bp.nbytes() / 1e6:.0f} MB ({bp.nbytes() / n_valid:.1f} B per event) "
+          f"in {(time.perf_counter() - t0) * 1e3:.0f} ms")
 
 
 if __name__ == "__main__":
