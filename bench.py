@@ -626,9 +626,11 @@ def run_ours(args):
         dom_bytes = stage_bytes.get(dom, 0.0)
         achieved = dom_bytes / (per_launch[dom] * 1e-3) / 1e9
         total_bytes = sum(ab.values())
-        traffic = None
+        traffic, issue = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            traffic = prof.get(dom)
+            issue = prof.get("_issue", {}).get(dom)         # ncu: the compute-side ceiling of this stage
         except Exception:
             pass
         stage_kernels = {
@@ -687,6 +689,7 @@ def run_ours(args):
                                         "note": "combined = max(HBM time of the algorithmic bytes, L2-atomic time of "
                                                 "3 vector-red requests per valid event at the measured request rate)"},
                          "event_kernels": ev_roof,
+                         "issue_bound_ncu": issue,
                          "note": "the dominant stage is the exact K-NN LUT build: a fixed per-window "
                                  "cost that is instruction/latency bound, not HBM bound",
                          "stage_ms_per_launch": per_launch,
