@@ -521,6 +521,9 @@ class BitpackedEvents:
                                self.max_count, self.skipped)
 
 
+_BITPACK_ONE_CALL_MAX_WORDS = 1 << 29      # 2 GiB of (mostly untouched) scratch at most
+
+
 def pack_events_bitpacked(events: torch.Tensor, num_pos_events: Optional[int], loss_or_cfg,
                           strict: bool = True) -> BitpackedEvents:
     """Loader-side builder of the bit-packed wire layout from an upstream-layout `[B, M, 6]` CPU
@@ -545,6 +548,10 @@ def pack_events_bitpacked(events: torch.Tensor, num_pos_events: Optional[int], l
     # one alignment word per run + the slack; untouched pages of it are never committed), then the
     # used part is copied out - cheaper than a sizing call, which repeats the pass over the rows
     cap = max(B * (3 * M + F + 2), 4)
+    if cap > _BITPACK_ONE_CALL_MAX_WORDS:                   # too much address space: size it exactly instead
+        cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, None, 0, p(fine), p(hdr), p(rword),
+                                                       p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")
+        cap = max(int(woff[-1]), 4)
     scratch = torch.empty(cap, dtype=torch.int32)
     cabi.check(lib.cmax_pack_events_host_bitpacked(cfg, p(ev), B, M, npos, p(scratch), cap, p(fine), p(hdr),
                                                    p(rword), p(woff), p(skipped)), "cmax_pack_events_host_bitpacked")

@@ -269,6 +269,13 @@ def test_bitpacked_host_packer_is_lossless(s, pab):
     T = int(c.sample_off[-1])
     assert np.array_equal(_decode_bitpacked(b), c.coords.numpy().view(np.uint32)[:T])
     assert b.max_count == c.max_count
+    # the sizing-call path (taken for very large batches) writes the same bytes as the one-call path
+    old_limit, io._BITPACK_ONE_CALL_MAX_WORDS = io._BITPACK_ONE_CALL_MAX_WORDS, 16
+    try:
+        b2 = io.pack_events_bitpacked(ev, npos, cfg)
+    finally:
+        io._BITPACK_ONE_CALL_MAX_WORDS = old_limit
+    assert all(torch.equal(getattr(b, k), getattr(b2, k)) for k in ("words", "run_hdr", "run_word", "word_off", "fine_start"))
     # a realistic window: well under 12 bytes per event
     ev2, npos2 = synthetic.make_event_batch(1, [300_000], 480, 640, 15, True, seed=2)
     big = io.pack_events_bitpacked(ev2, npos2, _cfg(dict(synthetic.DSEC_LOSS_CONFIG)))
